@@ -1,0 +1,129 @@
+"""Pin oracle/rerank_oracle.py against fixtures produced by the REAL reference
+(tests/golden/make_golden.py).  CPU only.
+
+Tolerances: the fixtures were made with the same torch build, so on the same CPU the
+match is bit-exact; another host CPU may pick another BLAS kernel (different fp32
+summation order), hence rtol 2e-5 on plans/scores and exact equality on iteration
+counts (cases were chosen with the stop test far from the 0.1 threshold).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import rerank_oracle as O
+from vitrerank import synth
+
+from golden.cases import CALC_CASES, LOOP_CASES
+
+RTOL = 2e-5
+ATOL = 1e-7
+
+
+def close(a, b, rtol=RTOL, atol=ATOL):
+    np.testing.assert_allclose(np.asarray(a), np.asarray(b), rtol=rtol, atol=atol)
+
+
+@pytest.fixture(scope="module")
+def G(golden_dir):
+    return {k: np.load(os.path.join(golden_dir, k + ".npz")) for k in
+            ("sinkhorn", "calc_similarity", "metrics", "loop")}
+
+
+@pytest.mark.parametrize("name", ["a", "b", "c"])
+def test_sinkhorn(G, name):
+    g = G["sinkhorn"]
+    seed, b, c, r, sigma, n_ref = [int(x) for x in g[f"{name}_meta"]]
+    gal = synth.make_gallery(b + 1, c, r, classes=2, seed=seed, sigma=sigma / 1000)
+    sim = O.patch_similarity(gal.patches[0], gal.patches[1:])
+    K = O.gibbs(sim)
+    u = gal.rollout[1:] / (gal.rollout[1:].sum(1, keepdim=True) + 1e-5)
+    v = (gal.rollout[0:1] / (gal.rollout[0:1].sum(1, keepdim=True) + 1e-5)).expand(b, -1).contiguous()
+    T, n_iter, errs = O.sinkhorn(K, u, v, trace=True)
+    assert n_iter == n_ref
+    close(T, g[f"{name}_T"])
+    Te, n_p, _ = O.sinkhorn_partial(K, u, v, ot_part=0.5, trace=True)
+    assert n_p == int(g[f"{name}_npartial"][0])
+    assert Te.shape == (b, r + 1, r + 1)
+    close(Te, g[f"{name}_Tpartial"])
+
+
+@pytest.mark.parametrize("case", CALC_CASES, ids=[c[0] for c in CALC_CASES])
+def test_calc_similarity(G, case):
+    name, seed, k, sigma, kw = case
+    g = G["calc_similarity"]
+    assert [int(x) for x in g[f"{name}_meta"]][:3] == [seed, k, int(sigma * 1000)]
+    gal = synth.make_gallery(k + 1, 128, 49, classes=2, seed=seed, sigma=sigma)
+    mode = O.select_mode(kw.get("use_uniform", False), kw.get("use_inverse", False),
+                         kw.get("use_minus", False), kw.get("use_soft", False))
+    score, uv, (n_iter, errs) = O.structural_similarity(
+        gal.patches[0], gal.centers[0], gal.patches[1:], gal.centers[1:], mode,
+        ot_temp=kw.get("ot_temp", 0.05), temperature=kw.get("temperature", 1.0),
+        use_cls_token=kw.get("use_cls_token", False), ot_part=kw.get("ot_part", 1.0), trace=True)
+    assert n_iter == int(g[f"{name}_meta"][3])
+    close(score, g[f"{name}_score"])
+    close(uv[0], g[f"{name}_u"])
+    close(uv[1], g[f"{name}_v"])
+    close(uv[2], g[f"{name}_T"])
+    close(uv[3], g[f"{name}_simr"])
+    if f"{name}_cc" in g.files:
+        close(uv[4], g[f"{name}_cc"], atol=1e-6)
+    else:
+        assert uv[4] is None
+
+
+def test_stage0(G):
+    g = G["calc_similarity"]
+    seed, k = [int(x) for x in g["stage0_meta"]]
+    gal = synth.make_gallery(k + 1, 128, 49, classes=2, seed=seed, sigma=0.6)
+    close(O.global_similarity(gal.centers[0], gal.centers), g["stage0_sim"], atol=1e-6)
+
+
+@pytest.mark.parametrize("name,kw", [("rollout", {}), ("rollout_iid", {}), ("rollout_part", dict(ot_part=0.3)),
+                                     ("rollout_uniform", dict(use_uniform=True))])
+def test_rollout(G, name, kw):
+    g = G["calc_similarity"]
+    seed, k, sigma, n_ref = [int(x) for x in g[f"{name}_meta"]]
+    if sigma < 0:
+        gal = synth.make_gallery(k + 1, 128, 49, classes=2, seed=seed, structured=False)
+    else:
+        gal = synth.make_gallery(k + 1, 128, 49, classes=2, seed=seed, sigma=sigma / 1000)
+    mode = "uniform" if kw.get("use_uniform") else "rollout"
+    score, uv, (n_iter, errs) = O.structural_similarity(
+        gal.patches[0], gal.centers[0], gal.patches[1:], gal.centers[1:], mode, ot_temp=0.05,
+        ot_part=kw.get("ot_part", 1.0), q_rollout=gal.rollout[0], c_rollout=gal.rollout[1:], trace=True)
+    assert n_iter == n_ref
+    close(score, g[f"{name}_score"])
+    close(uv[0], g[f"{name}_u"])
+    close(uv[1], g[f"{name}_v"])
+    close(uv[2], g[f"{name}_T"])
+    close(uv[3], g[f"{name}_simr"])
+
+
+def test_metrics_rank(G):
+    g = G["metrics"]
+    labels = torch.from_numpy(g["labels"])
+    for row, tops in zip(g["rows"], g["tops"]):
+        q = int(row[0])
+        r1, rp, mapr = O.metrics_rank(torch.from_numpy(tops), labels[q], labels)
+        assert r1 == row[1]
+        assert abs(rp - row[2]) < 1e-7
+        assert abs(mapr - row[3]) < 1e-6
+
+
+@pytest.mark.parametrize("case", LOOP_CASES, ids=[c[0] for c in LOOP_CASES])
+def test_query_loop(G, case):
+    name, n, classes, seed, sigma, truncs, use_rollout, flags = case
+    g = G["loop"]
+    gal = synth.make_gallery(n, 128, 49, classes=classes, seed=seed, sigma=sigma)
+    out = O.evaluate_banks(gal.patches, gal.centers, gal.rollout, gal.labels, trunc_nums=list(truncs),
+                           use_rollout=use_rollout, dump=True, **flags)
+    ref = g[f"{name}_metrics"]
+    close(out['r1'], ref[0], rtol=1e-9, atol=1e-9)
+    close(out['rp'], ref[1], rtol=1e-6)
+    close(out['mapr'], ref[2], rtol=1e-6)
+    tops = np.stack([d["top"].numpy() for d in out["dump"]])
+    assert np.array_equal(np.sort(tops, 1), np.sort(g[f"{name}_top"], 1))
+    close(np.stack([d["score"].numpy() for d in out["dump"]]), g[f"{name}_score"])
+    assert [d["n_iter"] for d in out["dump"]] == g[f"{name}_niter"].tolist()
