@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""Benchmark of the DIML rerank hot path (BASELINE.json metric: reranked query-candidate
+pairs/s at K=100).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A "step" is one full pass of the hot path: every gallery image is a query, the first stage
+shortlists K'=max(K, max num_pos) candidates, K=100 of them are reranked with Sinkhorn OT,
+blended, re-sorted and tallied into r1 / RP / MAP@R.  Default workload = BASELINE.json
+configs[1]: Cars196 test shape (8,131 images, 7x7 patches, embed_dim 128, rollout marginals).
+With N GPUs the queries of the SAME pass are sharded (interleaved) over the ranks, the
+gallery is replicated and only the tallies are all-reduced (NCCL) -> strong scaling.
+
+JSON line fields follow the driver contract; `value` is measured with the banks resident in
+HBM, `e2e` through the host-buffer entry (pinned host banks -> device, tallies -> host
+inside the timed region), `roofline` is for the dominant kernel (pair_fused_kernel) from CUDA
+events around its launch inside the timed steps, `cpu_baseline` is the oracle (torch CPU
+restatement of the reference loop) timed on this box's host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "vit-reranking_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+BYTES_PER_PAIR = {(128, 49): 25796, (768, 196): 605968}   # C*R*4 + C*4 + R*4
+WORKLOADS = {
+    # name: (synth shape name, K, flags, description)
+    "cars196": ("cars196", 100, dict(use_rollout=True, ot_part=1.0),
+                "Cars196 test shape: 8131 images, C=128, R=49 (7x7), top-100 OT rerank, rollout marginals"),
+    "cub200": ("cub200", 100, dict(use_rollout=True, ot_part=1.0),
+               "CUB-200 test shape: 5924 images, C=128, R=49, top-100 OT rerank, rollout marginals"),
+    "sop": ("sop", 100, dict(use_rollout=True, ot_part=1.0),
+            "SOP test shape: 60502 images, C=128, R=49, top-100 OT rerank, rollout marginals"),
+    "sop_k1000": ("sop", 1000, dict(use_inverse=True, temperature=0.1, use_cls_token=True, ot_part=1.0),
+                  "SOP shape, top-1000, calc_similarity + use_inverse T=0.1"),
+}
+METRIC = "reranked query-candidate pairs/sec at K=100"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                parts = [x.strip() for x in out.stdout.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = [float(r[0]) for r in self.rows if r[0].replace('.', '', 1).isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace('.', '', 1).isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def oracle_sample(gal, k, flags, budget_s, min_queries=16, seed=0):
+    """Time the oracle loop on uniformly sampled queries of the SAME workload until budget_s is spent."""
+    from oracle import rerank_oracle as O
+    n = gal.patches.shape[0]
+    torch.set_num_threads(os.cpu_count() or 1)
+    rng = np.random.default_rng(seed)
+    order = rng.permutation(n)
+    done, t0 = 0, time.perf_counter()
+    nit = []
+    batch = 8
+    while done < n:
+        q = order[done:done + batch]
+        out = O.evaluate_banks(gal.patches, gal.centers, gal.rollout, gal.labels, trunc_nums=[0, k],
+                               query_ids=q.tolist(), dump=True, **flags)
+        nit += [d["n_iter"] for d in out["dump"]]
+        done += len(q)
+        if time.perf_counter() - t0 > budget_s and done >= min_queries:
+            break
+    dt = time.perf_counter() - t0
+    return {"queries": done, "seconds": dt, "pairs_per_s": done * min(k, n - 0) / dt, "queries_per_s": done / dt,
+            "mean_niter": float(np.mean(nit)), "cores": torch.get_num_threads()}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path = the oracle port (the
+    reference is pure Python and cannot travel to this box; oracle/ is pinned against it by the
+    golden fixtures).  Rank 0 only."""
+    if rank != 0:
+        return
+    from vitrerank import synth
+    shape, k, flags, desc = WORKLOADS[args.workload]
+    gal = synth.make_named(shape, seed=0)
+    n = gal.patches.shape[0]
+    per_step_budget = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        oracle_sample(gal, k, flags, per_step_budget / 4, min_queries=4, seed=99)
+    res = [oracle_sample(gal, k, flags, per_step_budget, seed=i) for i in range(args.steps)]
+    tot_q = sum(r["queries"] for r in res)
+    tot_t = sum(r["seconds"] for r in res)
+    value = tot_q * k / tot_t
+    sample = f"{tot_q} uniformly sampled queries of {n} ({tot_q * k} pairs) over {args.steps} steps, {tot_t:.1f} s"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "k": k, "n": n, "queries_per_s": tot_q / tot_t,
+                   "mean_sinkhorn_iters": float(np.mean([r["mean_niter"] for r in res])),
+                   "note": "bounded sample per step; oracle port of the reference loop on host cores"},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": res[0]["cores"], "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cars196", choices=sorted(WORKLOADS))
+    ap.add_argument("--n", type=int, default=None, help="override gallery size (debug)")
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of oracle time for cpu_baseline")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from vitrerank import _lib, synth
+    from vitrerank.engine import OTParams, RerankEngine
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    shape, k, flags, desc = WORKLOADS[args.workload]
+    gal = synth.make_named(shape, seed=0, n=args.n)
+    n, c, r = gal.shape
+    params = OTParams.from_flags(**flags)
+    truncs = [0, k]
+    eng = RerankEngine.get(dev)
+    eng.register(gal.patches, gal.centers, gal.rollout, gal.labels)
+    kp = max(k, eng.bank["max_num_pos"], 8)
+    nq = (n - rank + world - 1) // world           # interleaved shard: queries rank, rank+world, ...
+    t_dev = torch.zeros(len(truncs), 8, dtype=torch.float64, device=dev)
+
+    def step(timers=None):
+        """One pass over this rank's query shard, banks resident in HBM."""
+        t_dev.zero_()
+        if timers:
+            timers[0].record()
+        idx, approx = eng.stage0_topk(kp, q_start=rank, q_stride=world, nq=nq)
+        if timers:
+            timers[1].record()
+        score, niter = eng.rerank_scores(idx, k, params, q_start=rank, q_stride=world)
+        if timers:
+            timers[2].record()
+        eng.finalize(idx, approx, score, k, truncs, q_start=rank, q_stride=world, tallies=t_dev)
+        if world > 1:
+            dist.all_reduce(t_dev)                  # the path's only exchange: 16 doubles
+        out = t_dev.cpu()                           # device -> host read of the tallies
+        if timers:
+            timers[3].record()
+        return out, niter
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        tallies, niter = step()
+    sync_all()
+    niter_np = niter.cpu().numpy()
+    _lib.take_launch_count()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        sync_all()
+        t_begin.record()
+        for s in range(args.steps):
+            tallies, niter = step(evs[s])
+        t_end.record()
+        sync_all()
+    launches = _lib.take_launch_count()
+    elapsed_ms = t_begin.elapsed_time(t_end)
+    t_el = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_el, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t_el.item())
+    pairs_per_step = n * min(k, n)
+    value = pairs_per_step * args.steps / (elapsed_ms / 1e3)
+    s0_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)
+    pf_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
+    fin_ms = statistics.mean(e[2].elapsed_time(e[3]) for e in evs)
+
+    # ---- end to end through the host-buffer entry ----
+    e2e = None
+    if not args.no_e2e:
+        pin = gal.pin()
+        h2d = sum(t.numel() * t.element_size() for t in (pin.patches, pin.centers, pin.rollout, pin.labels)) + n * 4
+        d2h = len(truncs) * 8 * 8
+        for _ in range(2):
+            eng.evaluate_host(pin.patches, pin.centers, pin.rollout, pin.labels, truncs, params, q_start=rank,
+                              q_stride=world, nq=nq)
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            tal_h = eng.evaluate_host(pin.patches, pin.centers, pin.rollout, pin.labels, truncs, params,
+                                      q_start=rank, q_stride=world, nq=nq)
+            if world > 1:
+                th = torch.from_numpy(tal_h).to(dev)
+                dist.all_reduce(th)
+                tal_h = th.cpu().numpy()
+        sync_all()
+        dt = time.perf_counter() - t0
+        t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        dt = float(t_e.item())
+        e2e = {"value": pairs_per_step * args.steps / dt, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * dt / args.steps,
+               "note": "vr_evaluate_host: pinned host banks -> HBM, S1..S5, tallies -> host; per rank"}
+        launches_e2e = _lib.take_launch_count()
+        eng.register(gal.patches, gal.centers, gal.rollout, gal.labels)
+    else:
+        launches_e2e = 0
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    bpp = BYTES_PER_PAIR.get((c, r), c * r * 4 + c * 4 + r * 4)
+    pairs_per_launch = nq * min(k, n)
+    achieved = pairs_per_launch * bpp / (pf_ms / 1e3) / 1e9
+    scale = n / 100.0
+    line = {
+        "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "n": n, "c": c, "r": r, "k": k, "kp": kp, "trunc_nums": truncs,
+                   "marginals": params.mode, "parallelism": f"queries sharded x{world}, gallery replicated",
+                   "queries_per_s": value / min(k, n), "l2": "inputs larger than L2 (patch bank %.0f MB)" %
+                   (gal.patches.numel() * 4 / 1e6),
+                   "sinkhorn_iters": {"mean": float(niter_np.mean()), "min": int(niter_np.min()),
+                                      "max": int(niter_np.max())},
+                   "stage_ms": {"stage0_topk": s0_ms, "pair_fused": pf_ms, "finalize_tally_d2h": fin_ms},
+                   "metrics": {"r1": (tallies[:, 0] / scale).tolist(), "rp": (tallies[:, 1] / scale).tolist(),
+                               "mapr": (tallies[:, 2] / scale).tolist()},
+                   "sm_count": eng.sm_count, "max_active_clusters": eng.max_active_clusters},
+        "roofline": {"bound": "hbm", "kernel": "pair_fused_kernel", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_pair": bpp, "pairs_per_launch": pairs_per_launch,
+                     "kernel_ms": pf_ms, "kernel_share_of_step": pf_ms / (elapsed_ms / args.steps)},
+        "clocks": clocks.summary(),
+        "gpu_launches": int(launches),
+    }
+    if e2e:
+        line["e2e"] = e2e
+        line["gpu_launches_e2e"] = int(launches_e2e)
+    # ---- CPU baseline: the oracle on this box's host cores, bounded sample ----
+    if world > 1:
+        dist.destroy_process_group()
+    if world == 1:
+        base = oracle_sample(gal, k, flags, args.cpu_budget)
+        line["cpu_baseline"] = {"value": base["pairs_per_s"], "unit": "pairs/s", "cores": base["cores"],
+                                "kind": "port",
+                                "sample": f"{base['queries']} uniformly sampled queries of {n} "
+                                          f"({base['queries'] * k} pairs), {base['seconds']:.1f} s, mean n*="
+                                          f"{base['mean_niter']:.1f}"}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,189 @@
+/*
+ * vitrerank.h -- C ABI of libvitrerank.so: the DIML structural-similarity rerank path of
+ * cazhang/vit-reranking as hand-written sm_100a CUDA kernels.
+ *
+ * The reference has no FFI: the path is plain Python functions (utilities/diml.py,
+ * evaluation/eval_cvt_diml.py, evaluation/metrics.py).  Each entry point below names the
+ * reference function (file:line under the reference checkout) whose arithmetic it
+ * replaces; the Python drop-in modules in vit-reranking_b200/{utilities,evaluation}/ keep
+ * the reference's names and signatures and call these through ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative VR_E_* code otherwise;
+ *     vr_last_error() returns a thread-local message for the last failure;
+ *   - all tensor arguments are raw DEVICE pointers to contiguous fp32 / int32 / int64
+ *     data unless the name ends in _host; the caller owns every buffer (inputs, outputs,
+ *     workspace); the library frees only what vr_create / vr_*_host allocated;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); no entry
+ *     point synchronises the host except the *_host ones, which return finished results;
+ *   - layouts follow the reference: patches [N, C, R] (R contiguous), centers [N, C],
+ *     rollout [N, R], labels [N] int64; sim / T matrices are [pairs, rows = candidate
+ *     patch, cols = query patch] (utilities/diml.py:100).
+ *   - no CPU fallback exists: without a CUDA device every compute entry fails.
+ */
+#ifndef VITRERANK_H_
+#define VITRERANK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VR_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define VR_API __attribute__((visibility("default")))
+#else
+#define VR_API
+#endif
+
+enum {
+    VR_OK = 0,
+    VR_E_INVALID = -1,   /* bad argument (shape, null pointer, unsupported size) */
+    VR_E_CUDA = -2,      /* a CUDA runtime call failed; message has the CUDA error */
+    VR_E_NOBANK = -3,    /* vr_bank_register has not been called on this context */
+    VR_E_WORKSPACE = -4  /* workspace too small; see the matching *_workspace_bytes */
+};
+
+/* Marginal modes: the branch order of utilities/diml.py:104-133 plus the rollout variant
+ * utilities/diml.py:344-354. */
+enum {
+    VR_MODE_ROLLOUT = 0, /* u,v = relu(rollout)/(sum+1e-5)            diml.py:351-354 */
+    VR_MODE_UNIFORM = 1, /* 1/R                                        diml.py:104-106 */
+    VR_MODE_INVERSE = 2, /* exp(-relu(cc)/temperature)/(sum+1e-5)      diml.py:107-113 */
+    VR_MODE_MINUS = 3,   /* (1-relu(cc))/(sum+1e-5)                    diml.py:114-121 */
+    VR_MODE_SOFT = 4,    /* softmax(cc)/(sum+1e-5)                     diml.py:122-127 */
+    VR_MODE_RELU = 5     /* relu(cc)/(sum+1e-5)                        diml.py:128-133 */
+};
+
+typedef struct vr_ot_params {
+    int32_t mode;          /* VR_MODE_* */
+    int32_t use_cls_token; /* cc modes: 1 = use the given centres, 0 = mean of patches (diml.py:87-96) */
+    float ot_temp;         /* Gibbs kernel temperature, 0.05 in evaluate (eval_cvt_diml.py:341) */
+    float temperature;     /* inverse-mode temperature (--temperature, diml.py:109) */
+    float ot_part;         /* > 0.999: full OT (diml.py:79,135); else one dummy point (diml.py:59-75) */
+    int32_t max_iter;      /* 100 (diml.py:42) */
+    float thresh;          /* 0.1, absolute, on the batch mean of |r - r_prev| (diml.py:45-52) */
+} vr_ot_params;
+
+typedef struct vr_ctx vr_ctx;
+
+/* Library / device -------------------------------------------------------------------- */
+VR_API int vr_abi_version(void);
+VR_API const char* vr_last_error(void);
+/* Creates a context bound to CUDA device `device` (queries SM count, cluster support). */
+VR_API int vr_create(int device, vr_ctx** out);
+VR_API int vr_destroy(vr_ctx* ctx);
+/* Number of SMs and the number of 8-CTA clusters of the fused pair kernel that can be
+ * co-resident (cudaOccupancyMaxActiveClusters); for reporting. */
+VR_API int vr_device_info(vr_ctx* ctx, int32_t* sm_count, int32_t* max_active_clusters);
+
+/* Gallery -----------------------------------------------------------------------------
+ * Replaces the bank construction at eval_cvt_diml.py:299-308 (banks are already
+ * L2-normalised by the caller as at :304-305).  rollout / labels / num_pos may be NULL
+ * when the mode / entry points used do not need them.  num_pos[i] = #{j : labels[j] ==
+ * labels[i]} (metrics.py:34), int32. */
+VR_API int vr_bank_register(vr_ctx* ctx, const float* patches, const float* centers, const float* rollout,
+                     const int64_t* labels, const int32_t* num_pos, int64_t n, int32_t c, int32_t r);
+
+/* S1: first-stage retrieval -----------------------------------------------------------
+ * Replaces, for a batch of queries, calc_similarity(stage=0) (diml.py:83-85), the self
+ * mask approx_sim[idx] = -100 (eval_cvt_diml.py:327) and the head of the full argsort
+ * (:329-332): out_idx[i, :] are the kp best gallery indices of query i in descending
+ * score order (ties: lower index first), out_score the matching fp32 scores; rows are
+ * padded with idx -1 when n < kp.  The N x N score matrix is never written to memory.
+ * Query i is gallery item q_start + i * q_stride (self-masked) when q_centers is NULL;
+ * otherwise q_centers is [nq, c] and self_idx (nullable, int64 [nq]) names the gallery
+ * item to mask for each query (the query != gallery case of training_tools/val.py:159-190). */
+VR_API size_t vr_stage0_workspace_bytes(vr_ctx* ctx, int64_t nq, int32_t kp);
+VR_API int vr_stage0_topk(vr_ctx* ctx, const float* q_centers, const int64_t* self_idx, int64_t q_start,
+                   int64_t q_stride, int64_t nq, int32_t kp, int32_t* out_idx, float* out_score,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* S2-S5a: structural scores of query/candidate pairs ------------------------------------
+ * Replaces the stage-1 call at eval_cvt_diml.py:334-351 for a batch of queries taken from
+ * the registered bank: candidate gather (:335-336,346-348), patch similarity
+ * (diml.py:100/:339), Gibbs kernel (:101-102/:341-342), marginals (:104-133/:344-354),
+ * Sinkhorn (:42-54, or Sinkhorn_partial :59-75 when ot_part <= 0.999) with its
+ * batch-global stop per query, and the score sum(T * sim) (:142-143/:361-362).
+ * cand_idx is [nq, cand_stride] int32 (first k entries of each row are used; -1 entries
+ * are skipped and score 0).  out_score is [nq, k]; out_niter (nullable) [nq] receives the
+ * number of Sinkhorn iterations each query ran. */
+VR_API size_t vr_rerank_workspace_bytes(vr_ctx* ctx, int64_t nq, int32_t k, const vr_ot_params* p);
+VR_API int vr_rerank_scores(vr_ctx* ctx, int64_t q_start, int64_t q_stride, int64_t nq, int32_t k,
+                     const int32_t* cand_idx, int32_t cand_stride, const vr_ot_params* p,
+                     float* out_score, int32_t* out_niter, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* S5b: blend, re-sort, metrics --------------------------------------------------------
+ * Replaces eval_cvt_diml.py:357-372 and evaluation/metrics.py:26-47 for a batch of
+ * queries: total = ot_score + approx_score, descending argsort (NaN first, ties: lower
+ * position first), and for every trunc t: final = reranked[:t] ++ approx_tops[t:]
+ * (t = 0: approx_tops), r1 / R-precision / MAP@R over final[:num_pos], plus Recall@1,2,4,8
+ * (extension).  approx_idx/approx_score are the [nq, kp] outputs of vr_stage0_topk (kp >=
+ * max(k, max num_pos) unless the gallery is smaller).  out_rank (nullable) [nq, k]
+ * receives the reranked candidate indices.  Adds into tallies [n_trunc, 8] doubles:
+ * sum r1, sum rp, sum mapr, sum R@1, R@2, R@4, R@8, query count (caller zeroes them). */
+VR_API size_t vr_finalize_workspace_bytes(vr_ctx* ctx, int64_t nq, int32_t n_trunc);
+VR_API int vr_finalize(vr_ctx* ctx, int64_t q_start, int64_t q_stride, int64_t nq, int32_t k, int32_t kp,
+                const int32_t* approx_idx, const float* approx_score, const float* ot_score,
+                const int32_t* trunc_nums_host, int32_t n_trunc, int32_t* out_rank, double* tallies,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* Direct calls (the per-call surface of utilities/diml.py) ------------------------------
+ * vr_sinkhorn replaces Sinkhorn(K, u, v, iter) (diml.py:42-54) for any [b, m, n] batch:
+ * T [b, m, n]; niter (nullable) one int32.  Workspace: vr_sinkhorn_workspace_bytes. */
+VR_API size_t vr_sinkhorn_workspace_bytes(int64_t b, int32_t m, int32_t n);
+VR_API int vr_sinkhorn(const float* K, const float* u, const float* v, int64_t b, int32_t m, int32_t n,
+                int32_t max_iter, float thresh, float* T, int32_t* niter, void* workspace,
+                size_t workspace_bytes, void* stream);
+
+/* vr_calc_similarity replaces stage 1 of calc_similarity (diml.py:86-147) and of
+ * calc_similarity_cvt_rollout (diml.py:331-366) for explicit tensors: anchor [c, r],
+ * anchor_center [c] (may be NULL in rollout/uniform mode), q_rollout [r] (rollout mode),
+ * fb [n, c, r], fb_center [n, c], c_rollout [n, r].  Outputs: score [n]; optional (NULL to
+ * skip) u [n, r], v [n, r], T [n, re, re] with re = r (full) or r + 1 (partial),
+ * sim_r [n, r, r], cc [n, r] (minus: cc_u; soft / relu: cc_v; other modes untouched),
+ * niter one int32.  The Sinkhorn stop is global over the n candidates, as in the reference. */
+VR_API size_t vr_calc_similarity_workspace_bytes(int64_t n, int32_t c, int32_t r, const vr_ot_params* p);
+VR_API int vr_calc_similarity(vr_ctx* ctx, const float* anchor, const float* anchor_center, const float* q_rollout,
+                       const float* fb, const float* fb_center, const float* c_rollout, int64_t n,
+                       int32_t c, int32_t r, const vr_ot_params* p, float* score, float* u, float* v,
+                       float* T, float* sim_r, float* cc, int32_t* niter, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+/* vr_global_similarity replaces calc_similarity(stage=0) (diml.py:83-85) for one query:
+ * sim[n] = sum_c q[c] * centers[n, c]. */
+VR_API int vr_global_similarity(const float* q_center, const float* centers, int64_t n, int32_t c, float* sim,
+                         void* stream);
+
+/* Whole pass with HOST buffers (the end-to-end entry) -----------------------------------
+ * Replaces the query loop eval_cvt_diml.py:308-372 over host-resident banks, as the
+ * reference keeps them (feature_bank and rollout_list live on the CPU, :278,:256): copies
+ * the banks to the device, runs S1..S5 for queries q_start + i * q_stride (i < nq) and
+ * returns tallies_host [n_trunc, 8] (same layout as vr_finalize; not yet divided by
+ * N/100).  per_query_niter_host (nullable) [nq].  Device memory is taken from an arena
+ * owned by ctx (grown on demand, released by vr_destroy).  Synchronous. */
+VR_API int vr_evaluate_host(vr_ctx* ctx, const float* patches_host, const float* centers_host,
+                     const float* rollout_host, const int64_t* labels_host, int64_t n, int32_t c, int32_t r,
+                     int64_t q_start, int64_t q_stride, int64_t nq, const int32_t* trunc_nums_host,
+                     int32_t n_trunc, const vr_ot_params* p, double* tallies_host,
+                     int32_t* per_query_niter_host);
+
+/* Same pass over the bank registered with vr_bank_register (device-resident inputs);
+ * tallies_host as above.  kp_hint = 0 lets the library size the first-stage shortlist
+ * from max_num_pos (the largest num_pos value, supplied by the caller). */
+VR_API int vr_evaluate_registered(vr_ctx* ctx, int64_t q_start, int64_t q_stride, int64_t nq,
+                           const int32_t* trunc_nums_host, int32_t n_trunc, int32_t max_num_pos,
+                           const vr_ot_params* p, double* tallies_host, int32_t* per_query_niter_host,
+                           void* stream);
+
+/* Number of kernels this library launched since the last call (resets the counter). */
+VR_API int64_t vr_take_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITRERANK_H_ */

@@ -205,7 +205,7 @@ def recall_at(tops, query_label, labels, ks=(1, 2, 4, 8)):
     return [1.0 if bool(hit[:k].any()) else 0.0 for k in ks]
 
 
-def evaluate_banks(patches, centers, rollout, labels, trunc_nums=None, use_rollout=True,
+def evaluate_banks(patches, centers, rollout, labels, trunc_nums=None, use_rollout=False,
                    use_uniform=False, use_inverse=False, temperature=1.0,
                    use_cls_token=False, use_minus=False, ot_part=0.1, query_ids=None,
                    dump=False):

@@ -1,0 +1,441 @@
+// C ABI of libvitrerank.so (see include/vitrerank.h for the contract and the reference
+// file:line each entry replaces).
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vr {
+
+static thread_local char g_err[512] = "";
+thread_local long long g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+}  // namespace vr
+
+struct vr_ctx {
+    int device = 0;
+    int sms = 0;
+    int max_clusters = 0;
+    // registered gallery (device pointers owned by the caller, or by the arena for *_host)
+    const float* patches = nullptr;
+    const float* centers = nullptr;
+    const float* rollout = nullptr;
+    const int64_t* labels = nullptr;
+    const int32_t* num_pos = nullptr;
+    int64_t n = 0;
+    int c = 0, r = 0;
+    // arena: named device buffers that only grow
+    std::unordered_map<std::string, std::pair<void*, size_t>> arena;
+    cudaStream_t own_stream = nullptr;
+};
+
+using namespace vr;
+
+static int arena_get(vr_ctx* ctx, const char* name, size_t bytes, void** out) {
+    auto& slot = ctx->arena[name];
+    if (slot.second < bytes || slot.first == nullptr) {
+        if (slot.first) VR_CHECK_CUDA(cudaFree(slot.first));
+        slot.first = nullptr;
+        slot.second = 0;
+        size_t want = align_up(bytes ? bytes : 256, 256);
+        VR_CHECK_CUDA(cudaMalloc(&slot.first, want));
+        slot.second = want;
+    }
+    *out = slot.first;
+    return VR_OK;
+}
+
+static int check_params(const vr_ot_params* p) {
+    VR_REQUIRE(p != nullptr, "ot params missing");
+    VR_REQUIRE(p->mode >= VR_MODE_ROLLOUT && p->mode <= VR_MODE_RELU, "unknown marginal mode %d", p->mode);
+    VR_REQUIRE(p->ot_temp > 0.f, "ot_temp must be positive");
+    VR_REQUIRE(p->max_iter >= 0 && p->max_iter <= 100000, "max_iter out of range");
+    VR_REQUIRE(p->ot_part > 0.999f || (p->ot_part >= 0.f && p->ot_part < 1.f), "ot_part must be in [0, 1]");
+    VR_REQUIRE(p->mode != VR_MODE_INVERSE || p->temperature != 0.f, "temperature must be non-zero");
+    return VR_OK;
+}
+
+extern "C" {
+
+int vr_abi_version(void) { return VR_ABI_VERSION; }
+
+const char* vr_last_error(void) { return g_err; }
+
+int64_t vr_take_launch_count(void) {
+    long long v = g_launches;
+    g_launches = 0;
+    return v;
+}
+
+int vr_create(int device, vr_ctx** out) {
+    VR_REQUIRE(out != nullptr, "vr_create: out is null");
+    int count = 0;
+    VR_CHECK_CUDA(cudaGetDeviceCount(&count));
+    VR_REQUIRE(device >= 0 && device < count, "vr_create: device %d not present (%d devices)", device, count);
+    VR_CHECK_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    VR_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+    VR_REQUIRE(prop.major == 10, "vr_create: device %d is sm_%d%d; this library is built for sm_100a only", device,
+               prop.major, prop.minor);
+    vr_ctx* ctx = new vr_ctx();
+    ctx->device = device;
+    ctx->sms = prop.multiProcessorCount;
+    int mc = 0;
+    int rc = pair_fused_max_clusters(&mc);
+    if (rc) {
+        delete ctx;
+        return rc;
+    }
+    ctx->max_clusters = mc;
+    rc = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess ? VR_OK : VR_E_CUDA;
+    if (rc) {
+        set_error("vr_create: cudaStreamCreate failed");
+        delete ctx;
+        return rc;
+    }
+    *out = ctx;
+    return VR_OK;
+}
+
+int vr_destroy(vr_ctx* ctx) {
+    if (!ctx) return VR_OK;
+    cudaSetDevice(ctx->device);
+    for (auto& kv : ctx->arena)
+        if (kv.second.first) cudaFree(kv.second.first);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return VR_OK;
+}
+
+int vr_device_info(vr_ctx* ctx, int32_t* sm_count, int32_t* max_active_clusters) {
+    VR_REQUIRE(ctx, "ctx is null");
+    if (sm_count) *sm_count = ctx->sms;
+    if (max_active_clusters) *max_active_clusters = ctx->max_clusters;
+    return VR_OK;
+}
+
+int vr_bank_register(vr_ctx* ctx, const float* patches, const float* centers, const float* rollout,
+                     const int64_t* labels, const int32_t* num_pos, int64_t n, int32_t c, int32_t r) {
+    VR_REQUIRE(ctx, "ctx is null");
+    VR_REQUIRE(patches && centers, "bank_register: patches and centers are required");
+    VR_REQUIRE(n > 0 && c > 0 && r > 0, "bank_register: bad shape [%lld, %d, %d]", (long long)n, c, r);
+    VR_REQUIRE(((uintptr_t)patches & 15) == 0 && ((uintptr_t)centers & 15) == 0, "bank_register: banks must be 16-byte aligned");
+    ctx->patches = patches;
+    ctx->centers = centers;
+    ctx->rollout = rollout;
+    ctx->labels = labels;
+    ctx->num_pos = num_pos;
+    ctx->n = n;
+    ctx->c = c;
+    ctx->r = r;
+    return VR_OK;
+}
+
+size_t vr_stage0_workspace_bytes(vr_ctx* ctx, int64_t nq, int32_t kp) {
+    if (!ctx || ctx->n <= 0) return 0;
+    return stage0_workspace_bytes(nq, ctx->n, kp, ctx->sms);
+}
+
+int vr_stage0_topk(vr_ctx* ctx, const float* q_centers, const int64_t* self_idx, int64_t q_start, int64_t q_stride,
+                   int64_t nq, int32_t kp, int32_t* out_idx, float* out_score, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+    VR_REQUIRE(ctx, "ctx is null");
+    if (!ctx->centers) {
+        set_error("stage0: no bank registered");
+        return VR_E_NOBANK;
+    }
+    VR_REQUIRE(out_idx && out_score, "stage0: outputs are null");
+    if (!q_centers)
+        VR_REQUIRE(q_start >= 0 && q_start + (nq - 1) * q_stride < ctx->n && q_start + (nq - 1) * q_stride >= 0,
+                   "stage0: query range outside the gallery");
+    VR_CHECK_CUDA(cudaSetDevice(ctx->device));
+    return stage0_topk(q_centers, self_idx, ctx->centers, q_start, q_stride, nq, ctx->n, ctx->c, kp, out_idx, out_score,
+                       workspace, workspace_bytes, ctx->sms, (cudaStream_t)stream);
+}
+
+size_t vr_rerank_workspace_bytes(vr_ctx* ctx, int64_t nq, int32_t k, const vr_ot_params* p) {
+    if (!ctx || !p || ctx->n <= 0) return 0;
+    if (pair_fused_supports(ctx->c, ctx->r, k)) return 256;
+    return generic_rerank_workspace_bytes(nq, k, ctx->r, p);
+}
+
+int vr_rerank_scores(vr_ctx* ctx, int64_t q_start, int64_t q_stride, int64_t nq, int32_t k, const int32_t* cand_idx,
+                     int32_t cand_stride, const vr_ot_params* p, float* out_score, int32_t* out_niter,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+    VR_REQUIRE(ctx, "ctx is null");
+    if (!ctx->patches) {
+        set_error("rerank: no bank registered");
+        return VR_E_NOBANK;
+    }
+    int rc = check_params(p);
+    if (rc) return rc;
+    VR_REQUIRE(nq > 0 && k > 0 && cand_idx && out_score && cand_stride >= k, "rerank: bad arguments");
+    VR_REQUIRE(p->mode != VR_MODE_ROLLOUT || ctx->rollout, "rerank: rollout mode needs a rollout bank");
+    VR_REQUIRE(q_start >= 0 && q_start + (nq - 1) * q_stride < ctx->n && q_start + (nq - 1) * q_stride >= 0,
+               "rerank: query range outside the gallery");
+    VR_CHECK_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pair_fused_supports(ctx->c, ctx->r, k)) {
+        PairArgs a{};
+        a.q_patches = ctx->patches;
+        a.q_centers = ctx->centers;
+        a.q_rollout = ctx->rollout;
+        a.c_patches = ctx->patches;
+        a.c_centers = ctx->centers;
+        a.c_rollout = ctx->rollout;
+        a.cand_idx = cand_idx;
+        a.cand_stride = cand_stride;
+        a.q_start = q_start;
+        a.q_stride = q_stride;
+        a.k = k;
+        a.p = *p;
+        a.out_score = out_score;
+        a.out_niter = out_niter;
+        return pair_fused_launch(a, nq, st);
+    }
+    GenArgs g{};
+    g.q_patches = ctx->patches;
+    g.q_centers = ctx->centers;
+    g.q_rollout = ctx->rollout;
+    g.c_patches = ctx->patches;
+    g.c_centers = ctx->centers;
+    g.c_rollout = ctx->rollout;
+    g.cand_idx = cand_idx;
+    g.cand_stride = cand_stride;
+    g.q_start = q_start;
+    g.q_stride = q_stride;
+    g.nq = nq;
+    g.k = k;
+    g.c = ctx->c;
+    g.r = ctx->r;
+    g.p = *p;
+    g.out_score = out_score;
+    g.out_niter = out_niter;
+    return generic_rerank(g, workspace, workspace_bytes, st);
+}
+
+size_t vr_finalize_workspace_bytes(vr_ctx* ctx, int64_t nq, int32_t n_trunc) {
+    (void)ctx;
+    return finalize_workspace_bytes(nq, n_trunc);
+}
+
+int vr_finalize(vr_ctx* ctx, int64_t q_start, int64_t q_stride, int64_t nq, int32_t k, int32_t kp,
+                const int32_t* approx_idx, const float* approx_score, const float* ot_score,
+                const int32_t* trunc_nums_host, int32_t n_trunc, int32_t* out_rank, double* tallies, void* workspace,
+                size_t workspace_bytes, void* stream) {
+    VR_REQUIRE(ctx, "ctx is null");
+    if (!ctx->labels || !ctx->num_pos) {
+        set_error("finalize: labels / num_pos not registered");
+        return VR_E_NOBANK;
+    }
+    VR_REQUIRE(approx_idx && approx_score && trunc_nums_host && tallies, "finalize: null argument");
+    VR_CHECK_CUDA(cudaSetDevice(ctx->device));
+    return finalize(q_start, q_stride, nq, k, kp, approx_idx, approx_score, ot_score, ctx->labels, ctx->num_pos,
+                    trunc_nums_host, n_trunc, out_rank, tallies, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+size_t vr_sinkhorn_workspace_bytes(int64_t b, int32_t m, int32_t n) { return generic_sinkhorn_workspace_bytes(b, m, n); }
+
+int vr_sinkhorn(const float* K, const float* u, const float* v, int64_t b, int32_t m, int32_t n, int32_t max_iter,
+                float thresh, float* T, int32_t* niter, void* workspace, size_t workspace_bytes, void* stream) {
+    VR_REQUIRE(K && u && v && T, "sinkhorn: null tensor");
+    return generic_sinkhorn(K, u, v, b, m, n, max_iter, thresh, T, niter, workspace, workspace_bytes,
+                            (cudaStream_t)stream);
+}
+
+size_t vr_calc_similarity_workspace_bytes(int64_t n, int32_t c, int32_t r, const vr_ot_params* p) {
+    if (!p) return 0;
+    if (n <= 0x7fffffff && pair_fused_supports(c, r, (int)n)) return 256;
+    return generic_rerank_workspace_bytes(1, (int)n, r, p);
+}
+
+int vr_calc_similarity(vr_ctx* ctx, const float* anchor, const float* anchor_center, const float* q_rollout,
+                       const float* fb, const float* fb_center, const float* c_rollout, int64_t n, int32_t c,
+                       int32_t r, const vr_ot_params* p, float* score, float* u, float* v, float* T, float* sim_r,
+                       float* cc, int32_t* niter, void* workspace, size_t workspace_bytes, void* stream) {
+    VR_REQUIRE(ctx, "ctx is null");
+    int rc = check_params(p);
+    if (rc) return rc;
+    VR_REQUIRE(anchor && fb && score, "calc_similarity: anchor, fb and score are required");
+    VR_REQUIRE(n > 0 && n < 0x7fffffff && c > 0 && r > 0, "calc_similarity: bad shape");
+    VR_REQUIRE((u == nullptr) == (v == nullptr), "calc_similarity: u and v go together");
+    const bool need_cc = p->mode >= VR_MODE_INVERSE;
+    VR_REQUIRE(!(need_cc && p->use_cls_token) || (anchor_center && fb_center),
+               "calc_similarity: centres required with use_cls_token");
+    VR_REQUIRE(p->mode != VR_MODE_ROLLOUT || (q_rollout && c_rollout), "calc_similarity: rollout marginals missing");
+    VR_CHECK_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pair_fused_supports(c, r, (int)n) && ((uintptr_t)anchor & 15) == 0 && ((uintptr_t)fb & 15) == 0) {
+        PairArgs a{};
+        a.q_patches = anchor;
+        a.q_centers = anchor_center;
+        a.q_rollout = q_rollout;
+        a.c_patches = fb;
+        a.c_centers = fb_center;
+        a.c_rollout = c_rollout;
+        a.cand_idx = nullptr;
+        a.cand_stride = (int)n;
+        a.q_start = 0;
+        a.q_stride = 0;
+        a.k = (int)n;
+        a.p = *p;
+        a.out_score = score;
+        a.out_niter = niter;
+        a.out_u = u;
+        a.out_v = v;
+        a.out_T = T;
+        a.out_simr = sim_r;
+        a.out_cc = cc;
+        return pair_fused_launch(a, 1, st);
+    }
+    GenArgs g{};
+    g.q_patches = anchor;
+    g.q_centers = anchor_center;
+    g.q_rollout = q_rollout;
+    g.c_patches = fb;
+    g.c_centers = fb_center;
+    g.c_rollout = c_rollout;
+    g.cand_idx = nullptr;
+    g.cand_stride = (int)n;
+    g.q_start = 0;
+    g.q_stride = 0;
+    g.nq = 1;
+    g.k = (int)n;
+    g.c = c;
+    g.r = r;
+    g.p = *p;
+    g.out_score = score;
+    g.out_niter = niter;
+    g.out_u = u;
+    g.out_v = v;
+    g.out_T = T;
+    g.out_simr = sim_r;
+    g.out_cc = cc;
+    return generic_rerank(g, workspace, workspace_bytes, st);
+}
+
+int vr_global_similarity(const float* q_center, const float* centers, int64_t n, int32_t c, float* sim, void* stream) {
+    VR_REQUIRE(q_center && centers && sim, "global_similarity: null tensor");
+    return global_similarity(q_center, centers, n, c, sim, (cudaStream_t)stream);
+}
+
+int vr_evaluate_registered(vr_ctx* ctx, int64_t q_start, int64_t q_stride, int64_t nq, const int32_t* trunc_nums_host,
+                           int32_t n_trunc, int32_t max_num_pos, const vr_ot_params* p, double* tallies_host,
+                           int32_t* per_query_niter_host, void* stream) {
+    VR_REQUIRE(ctx, "ctx is null");
+    if (!ctx->patches || !ctx->labels || !ctx->num_pos) {
+        set_error("evaluate: bank with labels and num_pos must be registered");
+        return VR_E_NOBANK;
+    }
+    int rc = check_params(p);
+    if (rc) return rc;
+    VR_REQUIRE(nq > 0 && trunc_nums_host && n_trunc >= 1 && n_trunc <= 16 && tallies_host, "evaluate: bad arguments");
+    VR_CHECK_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int kmax = 0;
+    for (int i = 0; i < n_trunc; i++) kmax = std::max(kmax, (int)trunc_nums_host[i]);
+    // eval_cvt_diml.py:332: top_inds = approx_tops[:max(trunc_nums)]; the gallery may be smaller
+    const int k = (int)std::min<int64_t>(kmax, ctx->n);
+    int kp = std::max(k, (int)std::min<int64_t>(max_num_pos, ctx->n));
+    kp = std::max(kp, (int)std::min<int64_t>(8, ctx->n));
+    std::vector<int32_t> truncs(n_trunc);
+    for (int i = 0; i < n_trunc; i++) truncs[i] = std::min((int)trunc_nums_host[i], k);
+
+    // chunk the queries so that per-chunk buffers stay bounded
+    int64_t chunk = std::min<int64_t>(nq, 16384);
+    const bool fused = k > 0 && pair_fused_supports(ctx->c, ctx->r, k);
+    if (k > 0 && !fused) {
+        size_t per_q = generic_rerank_workspace_bytes(1, k, ctx->r, p);
+        chunk = std::max<int64_t>(1, std::min<int64_t>(chunk, (int64_t)((size_t)1536 * 1024 * 1024 / per_q)));
+    }
+    void *d_idx, *d_sc, *d_ot, *d_nit, *d_tal, *d_ws0, *d_ws1, *d_ws2;
+    size_t ws0 = stage0_workspace_bytes(chunk, ctx->n, kp, ctx->sms);
+    size_t ws1 = k > 0 ? (fused ? 256 : generic_rerank_workspace_bytes(chunk, k, ctx->r, p)) : 256;
+    size_t ws2 = finalize_workspace_bytes(chunk, n_trunc);
+    if ((rc = arena_get(ctx, "ev_idx", (size_t)chunk * kp * 4, &d_idx))) return rc;
+    if ((rc = arena_get(ctx, "ev_sc", (size_t)chunk * kp * 4, &d_sc))) return rc;
+    if ((rc = arena_get(ctx, "ev_ot", (size_t)chunk * std::max(k, 1) * 4, &d_ot))) return rc;
+    if ((rc = arena_get(ctx, "ev_nit", (size_t)nq * 4, &d_nit))) return rc;
+    if ((rc = arena_get(ctx, "ev_tal", (size_t)n_trunc * 8 * sizeof(double), &d_tal))) return rc;
+    if ((rc = arena_get(ctx, "ev_ws0", ws0, &d_ws0))) return rc;
+    if ((rc = arena_get(ctx, "ev_ws1", ws1, &d_ws1))) return rc;
+    if ((rc = arena_get(ctx, "ev_ws2", ws2, &d_ws2))) return rc;
+    VR_CHECK_CUDA(cudaMemsetAsync(d_tal, 0, (size_t)n_trunc * 8 * sizeof(double), st));
+    VR_CHECK_CUDA(cudaMemsetAsync(d_nit, 0, (size_t)nq * 4, st));
+
+    for (int64_t lo = 0; lo < nq; lo += chunk) {
+        const int64_t cnt = std::min(chunk, nq - lo);
+        const int64_t qs = q_start + lo * q_stride;
+        rc = vr_stage0_topk(ctx, nullptr, nullptr, qs, q_stride, cnt, kp, (int32_t*)d_idx, (float*)d_sc, d_ws0, ws0, st);
+        if (rc) return rc;
+        if (k > 0) {
+            rc = vr_rerank_scores(ctx, qs, q_stride, cnt, k, (const int32_t*)d_idx, kp, p, (float*)d_ot,
+                                  (int32_t*)d_nit + lo, d_ws1, ws1, st);
+            if (rc) return rc;
+        }
+        rc = vr_finalize(ctx, qs, q_stride, cnt, k, kp, (const int32_t*)d_idx, (const float*)d_sc,
+                         k > 0 ? (const float*)d_ot : nullptr, truncs.data(), n_trunc, nullptr, (double*)d_tal, d_ws2,
+                         ws2, st);
+        if (rc) return rc;
+    }
+    VR_CHECK_CUDA(cudaMemcpyAsync(tallies_host, d_tal, (size_t)n_trunc * 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (per_query_niter_host)
+        VR_CHECK_CUDA(cudaMemcpyAsync(per_query_niter_host, d_nit, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    VR_CHECK_CUDA(cudaStreamSynchronize(st));
+    return VR_OK;
+}
+
+int vr_evaluate_host(vr_ctx* ctx, const float* patches_host, const float* centers_host, const float* rollout_host,
+                     const int64_t* labels_host, int64_t n, int32_t c, int32_t r, int64_t q_start, int64_t q_stride,
+                     int64_t nq, const int32_t* trunc_nums_host, int32_t n_trunc, const vr_ot_params* p,
+                     double* tallies_host, int32_t* per_query_niter_host) {
+    VR_REQUIRE(ctx, "ctx is null");
+    VR_REQUIRE(patches_host && centers_host && labels_host, "evaluate_host: patches, centers and labels are required");
+    VR_REQUIRE(n > 0 && c > 0 && r > 0, "evaluate_host: bad shape");
+    VR_CHECK_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->own_stream;
+    int rc;
+    void *d_p, *d_c, *d_r = nullptr, *d_l, *d_np;
+    const size_t bp = (size_t)n * c * r * 4, bc = (size_t)n * c * 4, br = (size_t)n * r * 4;
+    if ((rc = arena_get(ctx, "h_patches", bp, &d_p))) return rc;
+    if ((rc = arena_get(ctx, "h_centers", bc, &d_c))) return rc;
+    if (rollout_host && (rc = arena_get(ctx, "h_rollout", br, &d_r))) return rc;
+    if ((rc = arena_get(ctx, "h_labels", (size_t)n * 8, &d_l))) return rc;
+    if ((rc = arena_get(ctx, "h_numpos", (size_t)n * 4, &d_np))) return rc;
+    VR_CHECK_CUDA(cudaMemcpyAsync(d_p, patches_host, bp, cudaMemcpyHostToDevice, st));
+    VR_CHECK_CUDA(cudaMemcpyAsync(d_c, centers_host, bc, cudaMemcpyHostToDevice, st));
+    if (rollout_host) VR_CHECK_CUDA(cudaMemcpyAsync(d_r, rollout_host, br, cudaMemcpyHostToDevice, st));
+    VR_CHECK_CUDA(cudaMemcpyAsync(d_l, labels_host, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    // num_pos[i] = #{j : label[j] == label[i]}  (metrics.py:34), computed while the copies fly
+    std::unordered_map<int64_t, int32_t> hist;
+    hist.reserve((size_t)n / 2 + 16);
+    for (int64_t i = 0; i < n; i++) hist[labels_host[i]]++;
+    std::vector<int32_t> np((size_t)n);
+    int32_t max_np = 1;
+    for (int64_t i = 0; i < n; i++) {
+        np[i] = hist[labels_host[i]];
+        max_np = std::max(max_np, np[i]);
+    }
+    VR_CHECK_CUDA(cudaMemcpyAsync(d_np, np.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    VR_CHECK_CUDA(cudaStreamSynchronize(st));  // np lives on this stack frame
+    rc = vr_bank_register(ctx, (const float*)d_p, (const float*)d_c, (const float*)d_r, (const int64_t*)d_l,
+                          (const int32_t*)d_np, n, c, r);
+    if (rc) return rc;
+    return vr_evaluate_registered(ctx, q_start, q_stride, nq, trunc_nums_host, n_trunc, max_np, p, tallies_host,
+                                  per_query_niter_host, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,169 @@
+// S5b: blend + per-query re-sort + rank metrics, one warp per query.
+//
+// Replaces evaluation/eval_cvt_diml.py:357-372 (rank_in_tops = argsort(sim + approx_sim[top]),
+// final_tops = cat(top[rank][:t], approx_tops[t:])) and evaluation/metrics.py:26-47
+// (get_metrics_rank: r1, R-precision and MAP@R over final_tops[:num_pos], where num_pos
+// counts the query itself).  Recall@1/2/4/8 is an extension named by BASELINE.json.
+// Only final_tops[:num_pos] is ever read by the reference, so the first-stage shortlist of
+// length kp >= max(k, num_pos) carries everything needed; nothing N-long is materialised.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vr {
+
+constexpr int FN_WARPS = 4;
+constexpr int FN_METRICS = 8;  // r1, rp, mapr, R@1, R@2, R@4, R@8, count
+
+struct FinalizeArgs {
+    int64_t q_start, q_stride, nq;
+    int k, kp, n_trunc;
+    const int32_t* approx_idx;   // [nq, kp]
+    const float* approx_score;   // [nq, kp]
+    const float* ot_score;       // [nq, k] (nullptr when k == 0)
+    const int64_t* labels;       // [N]
+    const int32_t* num_pos;      // [N]
+    int32_t truncs[16];
+    int32_t* out_rank;           // [nq, k] or nullptr
+    double* per_query;           // [nq, n_trunc, FN_METRICS]
+};
+
+__global__ void __launch_bounds__(FN_WARPS * 32) finalize_kernel(FinalizeArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int k = a.k, kp = a.kp;
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw) + (size_t)warp * k;
+    int32_t* rer = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned long long*>(smem_raw) + (size_t)FN_WARPS * k) +
+                   (size_t)warp * k;
+    const int64_t qi = (int64_t)blockIdx.x * FN_WARPS + warp;
+    if (qi >= a.nq) return;
+    const int64_t qid = a.q_start + qi * a.q_stride;
+    const int32_t* aidx = a.approx_idx + qi * kp;
+    const float* asc = a.approx_score + qi * kp;
+    const int64_t ql = a.labels[qid];
+    const int np = a.num_pos[qid];
+
+    // number of valid shortlist entries (rows are padded with -1 when the gallery is small)
+    int nvalid = 0;
+    for (int e = lane; e < kp; e += 32) nvalid += (aidx[e] >= 0) ? 1 : 0;
+    nvalid = __reduce_add_sync(0xffffffffu, nvalid);
+    const int keff = min(k, nvalid);
+
+    // ---- blend + argsort(descending) by ranking (eval_cvt_diml.py:357) ----
+    for (int e = lane; e < keff; e += 32) keys[e] = pack_key(a.ot_score[qi * k + e] + asc[e], (uint32_t)e);
+    __syncwarp();
+    for (int e = lane; e < keff; e += 32) {
+        const unsigned long long me = keys[e];
+        int rank = 0;
+        for (int o = 0; o < keff; o++) rank += (keys[o] > me) ? 1 : 0;
+        rer[rank] = aidx[e];
+    }
+    __syncwarp();
+    if (a.out_rank)
+        for (int e = lane; e < k; e += 32) a.out_rank[qi * k + e] = e < keff ? rer[e] : -1;
+
+    // ---- metrics per trunc (metrics.py:26-47) ----
+    const int upto = min(np, nvalid);
+    for (int ti = 0; ti < a.n_trunc; ti++) {
+        const int t = a.truncs[ti];
+        const int tt = min(t, keff);  // entries taken from the reranked list
+        int cum = 0;                  // hits before the current 32-wide window
+        double ap = 0.0;
+        unsigned first8 = 0;
+        const int lim = max(upto, min(8, nvalid));  // Recall@8 looks at 8 entries even if num_pos < 8
+        for (int base = 0; base < lim; base += 32) {
+            const int j = base + lane;
+            bool hit = false;
+            if (j < lim) {
+                int src = -1;
+                if (j < tt) src = rer[j];
+                else {
+                    const int jj = j + (t - tt);  // cat(top[rank][:t], approx_tops[t:])
+                    src = jj < kp ? aidx[jj] : -1;
+                }
+                hit = src >= 0 && a.labels[src] == ql;
+            }
+            if (base == 0) first8 = __ballot_sync(0xffffffffu, hit) & 0xffu;
+            hit = hit && j < upto;
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (hit) {
+                const int c = cum + __popc(m & (0xffffffffu >> (31 - lane)));
+                ap += (double)((float)c / (float)(j + 1));
+            }
+            cum += __popc(m);
+        }
+        for (int o = 16; o > 0; o >>= 1) ap += __shfl_xor_sync(0xffffffffu, ap, o);
+        if (lane == 0) {
+            double* out = a.per_query + (qi * a.n_trunc + ti) * FN_METRICS;
+            out[0] = (first8 & 1u) ? 1.0 : 0.0;
+            out[1] = (double)((float)cum / (float)np);
+            out[2] = (double)(float)(ap / (double)np);
+            out[3] = (first8 & 0x1u) ? 1.0 : 0.0;
+            out[4] = (first8 & 0x3u) ? 1.0 : 0.0;
+            out[5] = (first8 & 0xfu) ? 1.0 : 0.0;
+            out[6] = (first8 & 0xffu) ? 1.0 : 0.0;
+            out[7] = 1.0;
+        }
+    }
+}
+
+// Deterministic column sums of per_query [nq, cols] into tallies[cols] (added).
+__global__ void __launch_bounds__(256) tally_kernel(const double* per_query, int64_t nq, int cols, double* tallies) {
+    __shared__ double red[256];
+    const int col = blockIdx.x;
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < nq; i += 256) s += per_query[i * cols + col];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tallies[col] += red[0];
+}
+
+size_t finalize_workspace_bytes(int64_t nq, int n_trunc) {
+    return align_up((size_t)nq * n_trunc * FN_METRICS * sizeof(double), 256) + 256;
+}
+
+int finalize(int64_t q_start, int64_t q_stride, int64_t nq, int k, int kp, const int32_t* approx_idx,
+             const float* approx_score, const float* ot_score, const int64_t* labels, const int32_t* num_pos,
+             const int32_t* truncs, int n_trunc, int32_t* out_rank, double* tallies, void* ws, size_t ws_bytes,
+             cudaStream_t st) {
+    VR_REQUIRE(nq > 0 && kp > 0 && k >= 0 && k <= kp, "finalize: bad sizes nq=%lld k=%d kp=%d", (long long)nq, k, kp);
+    VR_REQUIRE(n_trunc >= 1 && n_trunc <= 16, "finalize: 1..16 trunc values supported, got %d", n_trunc);
+    VR_REQUIRE(labels && num_pos, "finalize: labels / num_pos not registered");
+    VR_REQUIRE(k == 0 || ot_score, "finalize: ot_score missing");
+    if (finalize_workspace_bytes(nq, n_trunc) > ws_bytes) {
+        set_error("finalize: workspace %zu < %zu", ws_bytes, finalize_workspace_bytes(nq, n_trunc));
+        return VR_E_WORKSPACE;
+    }
+    FinalizeArgs a{};
+    a.q_start = q_start;
+    a.q_stride = q_stride;
+    a.nq = nq;
+    a.k = k;
+    a.kp = kp;
+    a.n_trunc = n_trunc;
+    a.approx_idx = approx_idx;
+    a.approx_score = approx_score;
+    a.ot_score = ot_score;
+    a.labels = labels;
+    a.num_pos = num_pos;
+    for (int i = 0; i < n_trunc; i++) {
+        VR_REQUIRE(truncs[i] >= 0 && truncs[i] <= k, "finalize: trunc %d outside 0..k=%d", truncs[i], k);
+        a.truncs[i] = truncs[i];
+    }
+    a.out_rank = out_rank;
+    a.per_query = reinterpret_cast<double*>(ws);
+    size_t smem = (size_t)FN_WARPS * k * (8 + 4) + 16;
+    VR_REQUIRE(smem <= 200 * 1024, "finalize: k=%d too large", k);
+    if (smem > 48 * 1024)
+        VR_CHECK_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    finalize_kernel<<<(unsigned)((nq + FN_WARPS - 1) / FN_WARPS), FN_WARPS * 32, smem, st>>>(a);
+    VR_LAUNCH_CHECK();
+    tally_kernel<<<n_trunc * FN_METRICS, 256, 0, st>>>(a.per_query, nq, n_trunc * FN_METRICS, tallies);
+    VR_LAUNCH_CHECK();
+    return VR_OK;
+}
+
+}  // namespace vr

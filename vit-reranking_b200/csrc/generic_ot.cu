@@ -1,0 +1,489 @@
+// Shape-generic OT path: any (C, R), any number of candidates per query, any [b, m, n] for
+// the direct Sinkhorn call.  Same arithmetic as pair_fused.cu, but the Gibbs kernel, sim and
+// the scaling vectors live in a caller-provided global workspace (L2-resident for typical
+// sizes) and the batch-global stop of utilities/diml.py:50-52 is taken between launches:
+//
+//   prepare   (1 launch)   sim, K(_ext), u, v per pair            diml.py:100-133 / :339-354
+//   iterate   (<= max_iter) r = u/(K c), c = v/(K^T r), sum|dr|   diml.py:47-49
+//   decide    (<= max_iter) per-query mean over all pairs < thresh -> done flag   :50-52
+//   finish    (1 launch)   T = r c^T * K, sim_r, score            diml.py:53,142-143
+//
+// iterate/decide pairs for iterations after a query stopped return immediately on its
+// `done` flag, so no host synchronisation is needed.  Used for everything the fused
+// R=49/C=128/K<=104 kernel does not cover (K=1000 shortlists, 14x14 grids, C=768, the
+// direct Sinkhorn() call).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vr {
+
+
+__device__ __forceinline__ float block_reduce_sum(float v, float* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = 0.f;
+    for (int i = 0; i < nw; i++) t += red[i];
+    return t;
+}
+__device__ __forceinline__ float block_reduce_max(float v, float* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = -INFINITY;
+    for (int i = 0; i < nw; i++) t = fmaxf(t, red[i]);
+    return t;
+}
+
+constexpr int GP_THREADS = 256;
+constexpr int GP_T = 64;   // output tile
+constexpr int GP_KC = 16;  // channels per step
+
+__global__ void __launch_bounds__(GP_THREADS) generic_prepare_kernel(GenArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* Fs = reinterpret_cast<float*>(smem_raw);  // [KC][T]
+    float* As = Fs + GP_KC * GP_T;                   // [KC][T]
+    float* red = As + GP_KC * GP_T;                  // [32]
+    float* qcs = red + 32;                           // [C]
+    float* gcs = qcs + a.c;                          // [C]
+    float* ccu = gcs + a.c;                          // [R]
+    float* ccv = ccu + a.r;                          // [R]
+
+    const int tid = threadIdx.x;
+    const int64_t pair = blockIdx.x;
+    const int64_t qi = pair / a.k;
+    const int pi = (int)(pair % a.k);
+    const int64_t qid = a.q_start + qi * a.q_stride;
+    const int C = a.c, R = a.r;
+    const bool full = a.p.ot_part > 0.999f;
+    const int Re = full ? R : R + 1;
+    const float bins = 1.0f - a.p.ot_part;
+    const int mode = a.p.mode;
+    if (pi == 0 && tid == 0) {
+        a.done[qi] = 0;
+        a.niter[qi] = 0;
+    }
+    const int cand = a.cand_idx ? a.cand_idx[qi * a.cand_stride + pi] : pi;
+    float* uo = a.u + pair * Re;
+    float* vo = a.v + pair * Re;
+    for (int i = tid; i < Re; i += GP_THREADS) {
+        a.rv[pair * Re + i] = 1.f;
+        a.cv[pair * Re + i] = 1.f;
+    }
+    if (tid == 0) a.e[pair] = 0.f;
+    if (cand < 0) {  // padded shortlist entry: a zero problem that never contributes
+        for (int i = tid; i < Re; i += GP_THREADS) {
+            uo[i] = 0.f;
+            vo[i] = 0.f;
+            a.rv[pair * Re + i] = 0.f;
+            a.cv[pair * Re + i] = 0.f;
+        }
+        for (int i = tid; i < Re * Re; i += GP_THREADS) a.K[pair * Re * Re + i] = 0.f;
+        for (int i = tid; i < R * R; i += GP_THREADS) a.sim[pair * R * R + i] = 0.f;
+        if (tid == 0) a.e[pair] = -1.f;  // marks the pair as skipped for iterate / decide
+        return;
+    }
+    const float* Ag = a.q_patches + qid * (int64_t)C * R;
+    const float* Fg = a.c_patches + (int64_t)cand * C * R;
+    float* simo = a.sim + pair * (int64_t)R * R;
+    float* Ko = a.K + pair * (int64_t)Re * Re;
+
+    // ---- sim[s][m] = sum_c F[c][s] * A[c][m], K = exp(-(1 - sim) / ot_temp) ----
+    const int tx = tid & 15, ty = tid >> 4;
+    for (int s0 = 0; s0 < R; s0 += GP_T) {
+        for (int m0 = 0; m0 < R; m0 += GP_T) {
+            float acc[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+            for (int c0 = 0; c0 < C; c0 += GP_KC) {
+                __syncthreads();
+                for (int e = tid; e < GP_KC * GP_T; e += GP_THREADS) {
+                    const int kk = e / GP_T, x = e % GP_T;
+                    const int c = c0 + kk;
+                    Fs[e] = (c < C && s0 + x < R) ? Fg[(int64_t)c * R + s0 + x] : 0.f;
+                    As[e] = (c < C && m0 + x < R) ? Ag[(int64_t)c * R + m0 + x] : 0.f;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int kk = 0; kk < GP_KC; kk++) {
+                    const float4 f = *reinterpret_cast<const float4*>(Fs + kk * GP_T + ty * 4);
+                    const float4 av = *reinterpret_cast<const float4*>(As + kk * GP_T + tx * 4);
+                    const float fv[4] = {f.x, f.y, f.z, f.w};
+                    const float aw[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) acc[i][j] = fmaf(fv[i], aw[j], acc[i][j]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int s = s0 + ty * 4 + i, m = m0 + tx * 4 + j;
+                    if (s < R && m < R) {
+                        simo[(int64_t)s * R + m] = acc[i][j];
+                        Ko[(int64_t)s * Re + m] = expf(-(1.0f - acc[i][j]) / a.p.ot_temp);
+                    }
+                }
+        }
+    }
+    if (!full) {  // utilities/diml.py:62-73
+        for (int i = tid; i < R; i += GP_THREADS) {
+            Ko[(int64_t)i * Re + R] = bins;
+            Ko[(int64_t)R * Re + i] = bins;
+        }
+        if (tid == 0) Ko[(int64_t)R * Re + R] = 0.f;
+    }
+
+    // ---- marginals ----
+    const bool need_cc = mode >= VR_MODE_INVERSE;
+    const bool cls = a.p.use_cls_token != 0;
+    if (need_cc) {
+        float nq = 0.f, ng = 0.f;
+        for (int c = tid; c < C; c += GP_THREADS) {
+            float x, g;
+            if (cls) {
+                x = a.q_centers[qid * C + c];
+                g = a.c_centers[(int64_t)cand * C + c];
+            } else {
+                float sx = 0.f, sg = 0.f;
+                for (int m = 0; m < R; m++) {
+                    sx += Ag[(int64_t)c * R + m];
+                    sg += Fg[(int64_t)c * R + m];
+                }
+                x = sx / (float)R;
+                g = sg / (float)R;
+            }
+            qcs[c] = x;
+            gcs[c] = g;
+            nq += x * x;
+            ng += g * g;
+        }
+        nq = block_reduce_sum(nq, red);
+        ng = block_reduce_sum(ng, red);
+        const float dq = fmaxf(sqrtf(nq), 1e-12f), dg = fmaxf(sqrtf(ng), 1e-12f);
+        for (int c = tid; c < C; c += GP_THREADS) {
+            qcs[c] = qcs[c] / dq;
+            gcs[c] = gcs[c] / dg;
+        }
+        __syncthreads();
+        for (int s = tid; s < R; s += GP_THREADS) {
+            float x = 0.f, y = 0.f;
+            for (int c = 0; c < C; c++) {
+                x = fmaf(qcs[c], Fg[(int64_t)c * R + s], x);
+                y = fmaf(Ag[(int64_t)c * R + s], gcs[c], y);
+            }
+            ccu[s] = x;
+            ccv[s] = y;
+        }
+        __syncthreads();
+    }
+    // numerators, strided over threads; sums via block reductions
+    float mu = 0.f, mv = 0.f;
+    if (mode == VR_MODE_SOFT) {
+        float lu = -INFINITY, lv = -INFINITY;
+        for (int s = tid; s < R; s += GP_THREADS) {
+            lu = fmaxf(lu, ccu[s]);
+            lv = fmaxf(lv, ccv[s]);
+        }
+        mu = block_reduce_max(lu, red);
+        mv = block_reduce_max(lv, red);
+    }
+    float su = 0.f, sv = 0.f;
+    for (int s = tid; s < R; s += GP_THREADS) {
+        float x, y;
+        switch (mode) {
+            case VR_MODE_UNIFORM: x = y = 1.0f / (float)R; break;
+            case VR_MODE_ROLLOUT:
+                x = fmaxf(a.c_rollout[(int64_t)cand * R + s], 0.f);
+                y = fmaxf(a.q_rollout[qid * R + s], 0.f);
+                break;
+            case VR_MODE_INVERSE:
+                x = expf(-fmaxf(ccu[s], 0.f) / a.p.temperature);
+                y = expf(-fmaxf(ccv[s], 0.f) / a.p.temperature);
+                break;
+            case VR_MODE_MINUS:
+                x = 1.f - fmaxf(ccu[s], 0.f);
+                y = 1.f - fmaxf(ccv[s], 0.f);
+                break;
+            case VR_MODE_SOFT:
+                x = expf(ccu[s] - mu);
+                y = expf(ccv[s] - mv);
+                break;
+            default:
+                x = fmaxf(ccu[s], 0.f);
+                y = fmaxf(ccv[s], 0.f);
+                break;
+        }
+        uo[s] = x;
+        vo[s] = y;
+        su += x;
+        sv += y;
+    }
+    su = block_reduce_sum(su, red);
+    sv = block_reduce_sum(sv, red);
+    if (mode == VR_MODE_SOFT) {  // softmax, then the common /(sum + 1e-5)
+        float s2u = 0.f, s2v = 0.f;
+        for (int s = tid; s < R; s += GP_THREADS) {
+            uo[s] = uo[s] / su;
+            vo[s] = vo[s] / sv;
+            s2u += uo[s];
+            s2v += vo[s];
+        }
+        su = block_reduce_sum(s2u, red);
+        sv = block_reduce_sum(s2v, red);
+    }
+    if (mode != VR_MODE_UNIFORM) {
+        su += 1e-5f;
+        sv += 1e-5f;
+        for (int s = tid; s < R; s += GP_THREADS) {
+            uo[s] = uo[s] / su;
+            vo[s] = vo[s] / sv;
+        }
+    }
+    if (!full && tid == 0) {
+        uo[R] = bins;
+        vo[R] = bins;
+    }
+    __syncthreads();
+    if (a.out_u)
+        for (int s = tid; s < R; s += GP_THREADS) {
+            a.out_u[pair * R + s] = uo[s];
+            a.out_v[pair * R + s] = vo[s];
+        }
+    if (a.out_cc && (mode == VR_MODE_MINUS || mode == VR_MODE_SOFT || mode == VR_MODE_RELU))
+        for (int s = tid; s < R; s += GP_THREADS) a.out_cc[pair * R + s] = (mode == VR_MODE_MINUS) ? ccu[s] : ccv[s];
+}
+
+// One Sinkhorn iteration for every pair whose query has not stopped.  rows x cols problem.
+struct IterArgs {
+    const float* K;   // [np, rows, cols]
+    const float* u;   // [np, rows]
+    const float* v;   // [np, cols]
+    float* rv;        // [np, rows]
+    float* cv;        // [np, cols]
+    float* e;         // [np]
+    int32_t* done;    // [nq]
+    int32_t* niter;   // [nq]
+    int rows, cols, k;
+    float thresh;
+};
+
+constexpr int GI_THREADS = 128;
+
+__global__ void __launch_bounds__(GI_THREADS) generic_iter_kernel(IterArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* cs = reinterpret_cast<float*>(smem_raw);  // [cols]
+    float* rs = cs + a.cols;                          // [rows]
+    float* red = rs + a.rows;                         // [32]
+    const int64_t pair = blockIdx.x;
+    const int64_t qi = pair / a.k;
+    if (a.done[qi] || a.e[pair] < 0.f) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rows = a.rows, cols = a.cols;
+    const float* K = a.K + pair * (int64_t)rows * cols;
+    const float* u = a.u + pair * rows;
+    const float* v = a.v + pair * cols;
+    float* rv = a.rv + pair * rows;
+    float* cv = a.cv + pair * cols;
+    for (int m = tid; m < cols; m += GI_THREADS) cs[m] = cv[m];
+    __syncthreads();
+    float e = 0.f;
+    for (int s = warp; s < rows; s += GI_THREADS / 32) {
+        float y = 0.f;
+        for (int m = lane; m < cols; m += 32) y = fmaf(K[(int64_t)s * cols + m], cs[m], y);
+        y = warp_sum(y);
+        if (lane == 0) {
+            const float rn = u[s] / y;
+            e += fabsf(rn - rv[s]);
+            rv[s] = rn;
+            rs[s] = rn;
+        }
+    }
+    __syncthreads();
+    for (int m = tid; m < cols; m += GI_THREADS) {
+        float x = 0.f;
+        for (int s = 0; s < rows; s++) x = fmaf(K[(int64_t)s * cols + m], rs[s], x);
+        cv[m] = v[m] / x;
+    }
+    e = block_reduce_sum(e, red);
+    if (tid == 0) a.e[pair] = e;
+}
+
+__global__ void __launch_bounds__(256) generic_decide_kernel(IterArgs a, int it) {
+    __shared__ float red[32];
+    const int64_t qi = blockIdx.x;
+    if (a.done[qi]) return;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < a.k; i += 256) s += fmaxf(a.e[qi * a.k + i], 0.f);
+    s = block_reduce_sum(s, red);
+    if (threadIdx.x == 0) {
+        a.niter[qi] = it + 1;
+        const float mean = s / ((float)a.k * (float)a.rows);
+        if (mean < a.thresh) a.done[qi] = 1;
+    }
+}
+
+struct FinishArgs {
+    const float* K;
+    const float* sim;  // [np, r, r] or nullptr
+    const float* rv;
+    const float* cv;
+    int rows, cols, r;
+    float* out_T;      // [np, rows, cols] or nullptr
+    float* out_simr;   // [np, r, r] or nullptr
+    float* out_score;  // [np] or nullptr
+};
+
+__global__ void __launch_bounds__(256) generic_finish_kernel(FinishArgs a) {
+    __shared__ float red[32];
+    const int64_t pair = blockIdx.x;
+    const int rows = a.rows, cols = a.cols, R = a.r;
+    const float* K = a.K + pair * (int64_t)rows * cols;
+    const float* rv = a.rv + pair * rows;
+    const float* cv = a.cv + pair * cols;
+    float sc = 0.f;
+    for (int i = threadIdx.x; i < rows * cols; i += 256) {
+        const int s = i / cols, m = i % cols;
+        const float T = (rv[s] * cv[m]) * K[i];
+        if (a.out_T) a.out_T[pair * (int64_t)rows * cols + i] = T;
+        if (a.sim && s < R && m < R) {
+            const float sr = T * a.sim[pair * (int64_t)R * R + (int64_t)s * R + m];
+            sc += sr;
+            if (a.out_simr) a.out_simr[pair * (int64_t)R * R + (int64_t)s * R + m] = sr;
+        }
+    }
+    if (a.out_score) {
+        sc = block_reduce_sum(sc, red);
+        if (threadIdx.x == 0) a.out_score[pair] = sc;
+    }
+}
+
+__global__ void generic_init_kernel(float* rv, float* cv, float* e, int64_t nr, int64_t nc, int64_t np, int32_t* done,
+                                    int32_t* niter, int64_t nq) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < np) e[i] = 0.f;
+    if (i < nr) rv[i] = 1.f;
+    if (i < nc) cv[i] = 1.f;
+    if (i < nq) {
+        done[i] = 0;
+        niter[i] = 0;
+    }
+}
+
+__global__ void copy_niter_kernel(const int32_t* src, int32_t* dst, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+
+// ---- workspace carving ----------------------------------------------------------------
+struct GenWs {
+    float *sim, *K, *u, *v, *rv, *cv, *e;
+    int32_t *done, *niter;
+    size_t bytes;
+};
+
+static GenWs carve(void* base, int64_t nq, int64_t np, int r, int rows, int cols, bool with_sim) {
+    GenWs w{};
+    size_t off = 0;
+    auto take = [&](size_t n) {
+        size_t o = off;
+        off = align_up(off + n, 256);
+        return base ? reinterpret_cast<unsigned char*>(base) + o : nullptr;
+    };
+    w.sim = reinterpret_cast<float*>(take(with_sim ? (size_t)np * r * r * 4 : 0));
+    w.K = reinterpret_cast<float*>(take(with_sim ? (size_t)np * rows * cols * 4 : 0));
+    w.u = reinterpret_cast<float*>(take(with_sim ? (size_t)np * rows * 4 : 0));
+    w.v = reinterpret_cast<float*>(take(with_sim ? (size_t)np * cols * 4 : 0));
+    w.rv = reinterpret_cast<float*>(take((size_t)np * rows * 4));
+    w.cv = reinterpret_cast<float*>(take((size_t)np * cols * 4));
+    w.e = reinterpret_cast<float*>(take((size_t)np * 4));
+    w.done = reinterpret_cast<int32_t*>(take((size_t)nq * 4));
+    w.niter = reinterpret_cast<int32_t*>(take((size_t)nq * 4));
+    w.bytes = off + 256;
+    return w;
+}
+
+size_t generic_rerank_workspace_bytes(int64_t nq, int k, int r, const vr_ot_params* p) {
+    const int re = (p->ot_part > 0.999f) ? r : r + 1;
+    return carve(nullptr, nq, nq * k, r, re, re, true).bytes;
+}
+
+size_t generic_sinkhorn_workspace_bytes(int64_t b, int m, int n) { return carve(nullptr, 1, b, 0, m, n, false).bytes; }
+
+static int run_iterations(const IterArgs& it, int64_t nq, int64_t np, int max_iter, cudaStream_t st) {
+    size_t smem = (size_t)(it.rows + it.cols + 32) * 4;
+    VR_REQUIRE(smem <= 48 * 1024, "sinkhorn: %d x %d too large", it.rows, it.cols);
+    for (int i = 0; i < max_iter; i++) {
+        generic_iter_kernel<<<(unsigned)np, GI_THREADS, smem, st>>>(it);
+        VR_LAUNCH_CHECK();
+        generic_decide_kernel<<<(unsigned)nq, 256, 0, st>>>(it, i);
+        VR_LAUNCH_CHECK();
+    }
+    return VR_OK;
+}
+
+int generic_rerank(GenArgs a, void* ws, size_t ws_bytes, cudaStream_t st) {
+    VR_REQUIRE(a.nq > 0 && a.k > 0, "generic_rerank: empty problem");
+    VR_REQUIRE(a.c >= 1 && a.r >= 1 && a.r <= 1024 && a.c <= 4096, "generic_rerank: unsupported shape C=%d R=%d", a.c,
+               a.r);
+    const int64_t np = a.nq * a.k;
+    VR_REQUIRE(np < 0x7fffffffll, "generic_rerank: too many pairs in one call (%lld)", (long long)np);
+    const int re = (a.p.ot_part > 0.999f) ? a.r : a.r + 1;
+    GenWs w = carve(ws, a.nq, np, a.r, re, re, true);
+    if (w.bytes > ws_bytes) {
+        set_error("generic_rerank: workspace %zu < %zu", ws_bytes, w.bytes);
+        return VR_E_WORKSPACE;
+    }
+    a.sim = w.sim; a.K = w.K; a.u = w.u; a.v = w.v; a.rv = w.rv; a.cv = w.cv; a.e = w.e;
+    a.done = w.done; a.niter = w.niter;
+    size_t smem = (size_t)(2 * GP_KC * GP_T + 32 + 2 * a.c + 2 * a.r) * 4;
+    if (smem > 48 * 1024)
+        VR_CHECK_CUDA(cudaFuncSetAttribute(generic_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    generic_prepare_kernel<<<(unsigned)np, GP_THREADS, smem, st>>>(a);
+    VR_LAUNCH_CHECK();
+    IterArgs it{w.K, w.u, w.v, w.rv, w.cv, w.e, w.done, w.niter, re, re, a.k, a.p.thresh};
+    int rc = run_iterations(it, a.nq, np, a.p.max_iter, st);
+    if (rc) return rc;
+    FinishArgs f{w.K, w.sim, w.rv, w.cv, re, re, a.r, a.out_T, a.out_simr, a.out_score};
+    generic_finish_kernel<<<(unsigned)np, 256, 0, st>>>(f);
+    VR_LAUNCH_CHECK();
+    if (a.out_niter) {
+        copy_niter_kernel<<<(unsigned)((a.nq + 255) / 256), 256, 0, st>>>(w.niter, a.out_niter, a.nq);
+        VR_LAUNCH_CHECK();
+    }
+    return VR_OK;
+}
+
+int generic_sinkhorn(const float* K, const float* u, const float* v, int64_t b, int m, int n, int max_iter,
+                     float thresh, float* T, int32_t* niter, void* ws, size_t ws_bytes, cudaStream_t st) {
+    VR_REQUIRE(b > 0 && m > 0 && n > 0 && b < 0x7fffffffll, "sinkhorn: bad shape [%lld, %d, %d]", (long long)b, m, n);
+    GenWs w = carve(ws, 1, b, 0, m, n, false);
+    if (w.bytes > ws_bytes) {
+        set_error("sinkhorn: workspace %zu < %zu", ws_bytes, w.bytes);
+        return VR_E_WORKSPACE;
+    }
+    const int64_t mx = b * (int64_t)(m > n ? m : n);
+    generic_init_kernel<<<(unsigned)((mx + 255) / 256), 256, 0, st>>>(w.rv, w.cv, w.e, b * m, b * n, b, w.done, w.niter, 1);
+    VR_LAUNCH_CHECK();
+    IterArgs it{K, u, v, w.rv, w.cv, w.e, w.done, w.niter, m, n, (int)b, thresh};
+    int rc = run_iterations(it, 1, b, max_iter, st);
+    if (rc) return rc;
+    FinishArgs f{K, nullptr, w.rv, w.cv, m, n, 0, T, nullptr, nullptr};
+    generic_finish_kernel<<<(unsigned)b, 256, 0, st>>>(f);
+    VR_LAUNCH_CHECK();
+    if (niter) {
+        copy_niter_kernel<<<1, 32, 0, st>>>(w.niter, niter, 1);
+        VR_LAUNCH_CHECK();
+    }
+    return VR_OK;
+}
+
+}  // namespace vr

@@ -1,0 +1,78 @@
+// Internal (non-ABI) interfaces between the translation units of libvitrerank.
+#pragma once
+#include "common.cuh"
+
+namespace vr {
+
+struct PairArgs {
+    const float* q_patches;   // query i block at q_patches + qid * C * R
+    const float* q_centers;   // + qid * C   (cc modes with use_cls_token)
+    const float* q_rollout;   // + qid * R   (rollout mode)
+    const float* c_patches;   // candidate banks, indexed by candidate id
+    const float* c_centers;
+    const float* c_rollout;
+    const int32_t* cand_idx;  // [nq, cand_stride] or nullptr (identity)
+    int cand_stride;
+    int64_t q_start, q_stride;
+    int k;
+    vr_ot_params p;
+    float* out_score;         // [nq, k]
+    int32_t* out_niter;       // [nq] or nullptr
+    float *out_u, *out_v, *out_T, *out_simr, *out_cc;  // optional, [nq*k, ...]
+};
+
+struct GenArgs {
+    const float* q_patches;
+    const float* q_centers;
+    const float* q_rollout;
+    const float* c_patches;
+    const float* c_centers;
+    const float* c_rollout;
+    const int32_t* cand_idx;
+    int cand_stride;
+    int64_t q_start, q_stride, nq;
+    int k, c, r;
+    vr_ot_params p;
+    // workspace
+    float* sim;    // [np, r, r]
+    float* K;      // [np, re, re]
+    float* u;      // [np, re]
+    float* v;      // [np, re]
+    float* rv;     // [np, rows]
+    float* cv;     // [np, cols]
+    float* e;      // [np]
+    int32_t* done; // [nq]
+    int32_t* niter;// [nq]
+    // outputs
+    float* out_score;
+    int32_t* out_niter;
+    float *out_u, *out_v, *out_T, *out_simr, *out_cc;
+};
+
+// stage0_topk.cu
+size_t stage0_workspace_bytes(int64_t nq, int64_t n, int kp, int sms);
+int stage0_topk(const float* q_centers, const int64_t* self_idx, const float* centers, int64_t q_start,
+                int64_t q_stride, int64_t nq, int64_t n, int c, int kp, int32_t* out_idx, float* out_score,
+                void* ws, size_t ws_bytes, int sms, cudaStream_t st);
+int global_similarity(const float* q, const float* centers, int64_t n, int c, float* sim, cudaStream_t st);
+
+// pair_fused.cu
+int pair_fused_max_clusters(int* out);
+bool pair_fused_supports(int c, int r, int k);
+int pair_fused_launch(const PairArgs& a, int64_t nq, cudaStream_t st);
+
+// generic_ot.cu
+size_t generic_rerank_workspace_bytes(int64_t nq, int k, int r, const vr_ot_params* p);
+size_t generic_sinkhorn_workspace_bytes(int64_t b, int m, int n);
+int generic_rerank(GenArgs a, void* ws, size_t ws_bytes, cudaStream_t st);
+int generic_sinkhorn(const float* K, const float* u, const float* v, int64_t b, int m, int n, int max_iter,
+                     float thresh, float* T, int32_t* niter, void* ws, size_t ws_bytes, cudaStream_t st);
+
+// finalize.cu
+size_t finalize_workspace_bytes(int64_t nq, int n_trunc);
+int finalize(int64_t q_start, int64_t q_stride, int64_t nq, int k, int kp, const int32_t* approx_idx,
+             const float* approx_score, const float* ot_score, const int64_t* labels, const int32_t* num_pos,
+             const int32_t* truncs, int n_trunc, int32_t* out_rank, double* tallies, void* ws, size_t ws_bytes,
+             cudaStream_t st);
+
+}  // namespace vr

@@ -1,0 +1,296 @@
+"""Host side of the B200 rerank path: torch owns device memory and streams, every
+computation goes through the C ABI of libvitrerank.so (no torch math on the path).
+
+Mirrors the query loop of the reference (evaluation/eval_cvt_diml.py:308-416) as a batched
+pipeline over the registered gallery:
+
+    S1  stage0_topk      global cosine + self mask + top-K' select      (:325-332)
+    S2-S5a rerank_scores gather + patch sim + Sinkhorn + score          (:334-351)
+    S5b finalize         blend, re-sort, r1 / RP / MAP@R tallies        (:357-372)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import OTParamsStruct, VR_MODE, check, lib
+
+METRIC_COLS = ("r1", "rp", "mapr", "recall@1", "recall@2", "recall@4", "recall@8", "count")
+
+
+@dataclasses.dataclass
+class OTParams:
+    mode: str = "rollout"          # rollout | uniform | inverse | minus | soft | relu
+    use_cls_token: bool = False
+    ot_temp: float = 0.05          # eval_cvt_diml.py:341 / diml.py:325
+    temperature: float = 1.0       # diml.py:77 default; --temperature 0.1 in the north-star run
+    ot_part: float = 1.0
+    max_iter: int = 100            # diml.py:42
+    thresh: float = 1e-1           # diml.py:45
+
+    def struct(self) -> OTParamsStruct:
+        return OTParamsStruct(VR_MODE[self.mode], int(self.use_cls_token), float(self.ot_temp),
+                              float(self.temperature), float(self.ot_part), int(self.max_iter),
+                              float(self.thresh))
+
+    @staticmethod
+    def from_flags(use_rollout=False, use_uniform=False, use_inverse=False, use_minus=False, use_soft=False,
+                   temperature=1.0, use_cls_token=False, ot_part=1.0, ot_temp=0.05) -> "OTParams":
+        """Branch order of evaluate (eval_cvt_diml.py:201,334-351) and of calc_similarity
+        (diml.py:80-81,104-133): with use_rollout the rollout branch runs and ignores the
+        cross-correlation flags."""
+        if use_minus:
+            use_inverse = False
+        if use_uniform:
+            mode = "uniform"
+        elif use_rollout:
+            mode = "rollout"
+        elif use_inverse:
+            mode = "inverse"
+        elif use_minus:
+            mode = "minus"
+        elif use_soft:
+            mode = "soft"
+        else:
+            mode = "relu"
+        return OTParams(mode=mode, use_cls_token=use_cls_token, ot_temp=ot_temp, temperature=temperature,
+                        ot_part=ot_part)
+
+
+def _ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _f32(t, device):
+    if t is None:
+        return None
+    return t.to(device=device, dtype=torch.float32).contiguous()
+
+
+def require_cuda(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise _lib.VitRerankError("vitrerank needs a CUDA device (B200, sm_100a); there is no CPU path")
+    dev = torch.device(device if device is not None else "cuda")
+    if dev.type != "cuda":
+        raise _lib.VitRerankError(f"vitrerank runs on CUDA devices only, got {dev}")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+class RerankEngine:
+    """One context per CUDA device."""
+
+    _instances: dict = {}
+
+    def __init__(self, device=None):
+        self.device = require_cuda(device)
+        h = C.c_void_p()
+        check(lib.vr_create(self.device.index, C.byref(h)), "vr_create")
+        self._h = h
+        self._bank = None
+        self._ws = {}
+        sm, mc = C.c_int32(), C.c_int32()
+        check(lib.vr_device_info(self._h, C.byref(sm), C.byref(mc)))
+        self.sm_count, self.max_active_clusters = sm.value, mc.value
+
+    @classmethod
+    def get(cls, device=None) -> "RerankEngine":
+        dev = require_cuda(device)
+        if dev.index not in cls._instances:
+            cls._instances[dev.index] = cls(dev)
+        return cls._instances[dev.index]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.vr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- gallery -----------------------------------------------------------------------
+    def register(self, patches, centers, rollout=None, labels=None):
+        """patches [N,C,R], centers [N,C], rollout [N,R], labels [N]; moved to the device if
+        needed (the reference keeps the patch bank on the host, eval_cvt_diml.py:278)."""
+        dev = self.device
+        patches, centers, rollout = _f32(patches, dev), _f32(centers, dev), _f32(rollout, dev)
+        n, c, r = patches.shape
+        num_pos = None
+        max_np = 1
+        if labels is not None:
+            labels = labels.to(device=dev, dtype=torch.int64).contiguous()
+            _, inv, cnt = torch.unique(labels, return_inverse=True, return_counts=True)
+            num_pos = cnt[inv].to(torch.int32).contiguous()   # metrics.py:34 (counts the query itself)
+            max_np = int(cnt.max().item())
+        check(lib.vr_bank_register(self._h, _ptr(patches), _ptr(centers), _ptr(rollout), _ptr(labels),
+                                   _ptr(num_pos), n, c, r), "vr_bank_register")
+        self._bank = dict(patches=patches, centers=centers, rollout=rollout, labels=labels, num_pos=num_pos,
+                          n=n, c=c, r=r, max_num_pos=max_np)
+        return self
+
+    @property
+    def bank(self):
+        if self._bank is None:
+            raise _lib.VitRerankError("no gallery registered")
+        return self._bank
+
+    def _workspace(self, name, nbytes):
+        t = self._ws.get(name)
+        if t is None or t.numel() < nbytes:
+            t = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+            self._ws[name] = t
+        return t
+
+    # ---- S1 ------------------------------------------------------------------------------
+    def stage0_topk(self, kp, q_start=0, q_stride=1, nq=None, q_centers=None, self_idx=None):
+        b = self.bank
+        if q_centers is not None:
+            q_centers = _f32(q_centers, self.device)
+            nq = q_centers.shape[0]
+            if self_idx is not None:
+                self_idx = self_idx.to(device=self.device, dtype=torch.int64).contiguous()
+        elif nq is None:
+            nq = (b["n"] - q_start + q_stride - 1) // q_stride
+        idx = torch.empty(nq, kp, dtype=torch.int32, device=self.device)
+        score = torch.empty(nq, kp, dtype=torch.float32, device=self.device)
+        nb = lib.vr_stage0_workspace_bytes(self._h, nq, kp)
+        ws = self._workspace("s0", nb)
+        check(lib.vr_stage0_topk(self._h, _ptr(q_centers), _ptr(self_idx), q_start, q_stride, nq, kp, _ptr(idx),
+                                 _ptr(score), _ptr(ws), ws.numel(), _stream(self.device)), "vr_stage0_topk")
+        return idx, score
+
+    # ---- S2-S5a ----------------------------------------------------------------------------
+    def rerank_scores(self, cand_idx, k, params: OTParams, q_start=0, q_stride=1):
+        cand_idx = cand_idx.to(device=self.device, dtype=torch.int32).contiguous()
+        nq, stride = cand_idx.shape
+        ps = params.struct()
+        score = torch.empty(nq, k, dtype=torch.float32, device=self.device)
+        niter = torch.zeros(nq, dtype=torch.int32, device=self.device)
+        nb = lib.vr_rerank_workspace_bytes(self._h, nq, k, C.byref(ps))
+        ws = self._workspace("s1", nb)
+        check(lib.vr_rerank_scores(self._h, q_start, q_stride, nq, k, _ptr(cand_idx), stride, C.byref(ps),
+                                   _ptr(score), _ptr(niter), _ptr(ws), ws.numel(), _stream(self.device)),
+              "vr_rerank_scores")
+        return score, niter
+
+    # ---- S5b ---------------------------------------------------------------------------------
+    def finalize(self, approx_idx, approx_score, ot_score, k, trunc_nums, q_start=0, q_stride=1, tallies=None,
+                 want_rank=False):
+        nq, kp = approx_idx.shape
+        nt = len(trunc_nums)
+        if tallies is None:
+            tallies = torch.zeros(nt, 8, dtype=torch.float64, device=self.device)
+        rank = torch.empty(nq, k, dtype=torch.int32, device=self.device) if (want_rank and k > 0) else None
+        tr = (C.c_int32 * nt)(*[int(t) for t in trunc_nums])
+        nb = lib.vr_finalize_workspace_bytes(self._h, nq, nt)
+        ws = self._workspace("s2", nb)
+        check(lib.vr_finalize(self._h, q_start, q_stride, nq, k, kp, _ptr(approx_idx), _ptr(approx_score),
+                              _ptr(ot_score), tr, nt, _ptr(rank), _ptr(tallies), _ptr(ws), ws.numel(),
+                              _stream(self.device)), "vr_finalize")
+        return tallies, rank
+
+    # ---- whole pass over the registered (device-resident) gallery ---------------------------------
+    def evaluate(self, trunc_nums, params: OTParams, q_start=0, q_stride=1, nq=None, want_niter=False):
+        """Tallies [len(trunc_nums), 8] (numpy float64, columns METRIC_COLS; sums, not yet
+        divided by N/100) for queries q_start + i*q_stride."""
+        b = self.bank
+        if nq is None:
+            nq = (b["n"] - q_start + q_stride - 1) // q_stride
+        nt = len(trunc_nums)
+        tr = (C.c_int32 * nt)(*[int(t) for t in trunc_nums])
+        out = np.zeros((nt, 8), dtype=np.float64)
+        nit = np.zeros(nq, dtype=np.int32) if want_niter else None
+        ps = params.struct()
+        check(lib.vr_evaluate_registered(self._h, q_start, q_stride, nq, tr, nt, b["max_num_pos"], C.byref(ps),
+                                         out.ctypes.data_as(C.POINTER(C.c_double)),
+                                         C.c_void_p(nit.ctypes.data if nit is not None else 0),
+                                         _stream(self.device)), "vr_evaluate_registered")
+        return (out, nit) if want_niter else out
+
+    # ---- whole pass from HOST buffers (end-to-end entry) ---------------------------------------
+    def evaluate_host(self, patches, centers, rollout, labels, trunc_nums, params: OTParams, q_start=0,
+                      q_stride=1, nq=None, want_niter=False):
+        """Same as evaluate() but the banks are CPU tensors (pinned for full PCIe speed), as the
+        reference keeps them; host->device copies and the device->host read of the tallies are
+        inside the call."""
+        for t in (patches, centers, labels):
+            if t.device.type != "cpu":
+                raise _lib.VitRerankError("evaluate_host takes CPU tensors")
+        patches = patches.contiguous().float()
+        centers = centers.contiguous().float()
+        rollout = None if rollout is None else rollout.contiguous().float()
+        labels = labels.contiguous().long()
+        n, c, r = patches.shape
+        if nq is None:
+            nq = (n - q_start + q_stride - 1) // q_stride
+        nt = len(trunc_nums)
+        tr = (C.c_int32 * nt)(*[int(t) for t in trunc_nums])
+        out = np.zeros((nt, 8), dtype=np.float64)
+        nit = np.zeros(nq, dtype=np.int32) if want_niter else None
+        ps = params.struct()
+        check(lib.vr_evaluate_host(self._h, _ptr(patches), _ptr(centers), _ptr(rollout), _ptr(labels), n, c, r,
+                                   q_start, q_stride, nq, tr, nt, C.byref(ps),
+                                   out.ctypes.data_as(C.POINTER(C.c_double)),
+                                   C.c_void_p(nit.ctypes.data if nit is not None else 0)), "vr_evaluate_host")
+        self._bank = None  # the context now points at its own copy of the banks
+        return (out, nit) if want_niter else out
+
+    # ---- direct calls (utilities/diml.py surface) ---------------------------------------------------
+    def sinkhorn(self, K, u, v, max_iter=100, thresh=1e-1):
+        K, u, v = _f32(K, self.device), _f32(u, self.device), _f32(v, self.device)
+        b, m, n = K.shape
+        T = torch.empty_like(K)
+        niter = torch.zeros(1, dtype=torch.int32, device=self.device)
+        nb = lib.vr_sinkhorn_workspace_bytes(b, m, n)
+        ws = self._workspace("sk", nb)
+        check(lib.vr_sinkhorn(_ptr(K), _ptr(u), _ptr(v), b, m, n, int(max_iter), float(thresh), _ptr(T),
+                              _ptr(niter), _ptr(ws), ws.numel(), _stream(self.device)), "vr_sinkhorn")
+        return T, niter
+
+    def global_similarity(self, q_center, centers):
+        q_center, centers = _f32(q_center, self.device), _f32(centers, self.device)
+        n, c = centers.shape
+        sim = torch.empty(n, dtype=torch.float32, device=self.device)
+        check(lib.vr_global_similarity(_ptr(q_center), _ptr(centers), n, c, _ptr(sim), _stream(self.device)),
+              "vr_global_similarity")
+        return sim
+
+    def calc_similarity(self, anchor, anchor_center, fb, fb_center, params: OTParams, q_rollout=None,
+                        c_rollout=None, want_uv=True):
+        dev = self.device
+        anchor, fb = _f32(anchor, dev), _f32(fb, dev)
+        anchor_center, fb_center = _f32(anchor_center, dev), _f32(fb_center, dev)
+        q_rollout, c_rollout = _f32(q_rollout, dev), _f32(c_rollout, dev)
+        n, c, r = fb.shape
+        assert anchor.shape == (c, r), f"anchor {tuple(anchor.shape)} vs fb {tuple(fb.shape)}"
+        re = r if params.ot_part > 0.999 else r + 1
+        score = torch.empty(n, dtype=torch.float32, device=dev)
+        niter = torch.zeros(1, dtype=torch.int32, device=dev)
+        u = v = T = sim_r = cc = None
+        if want_uv:
+            u = torch.empty(n, r, dtype=torch.float32, device=dev)
+            v = torch.empty(n, r, dtype=torch.float32, device=dev)
+            T = torch.empty(n, re, re, dtype=torch.float32, device=dev)
+            sim_r = torch.empty(n, r, r, dtype=torch.float32, device=dev)
+            if params.mode in ("minus", "soft", "relu"):
+                cc = torch.empty(n, r, dtype=torch.float32, device=dev)
+        ps = params.struct()
+        nb = lib.vr_calc_similarity_workspace_bytes(n, c, r, C.byref(ps))
+        ws = self._workspace("cs", nb)
+        check(lib.vr_calc_similarity(self._h, _ptr(anchor), _ptr(anchor_center), _ptr(q_rollout), _ptr(fb),
+                                     _ptr(fb_center), _ptr(c_rollout), n, c, r, C.byref(ps), _ptr(score), _ptr(u),
+                                     _ptr(v), _ptr(T), _ptr(sim_r), _ptr(cc), _ptr(niter), _ptr(ws), ws.numel(),
+                                     _stream(dev)), "vr_calc_similarity")
+        return score, (u, v, T, sim_r, cc), niter
