@@ -35,14 +35,21 @@ EPS = 1e-5               # diml.py:110 and friends
 MODES = ("rollout", "uniform", "inverse", "minus", "soft", "relu")
 
 
-def sinkhorn(K, u, v, max_iter=SINKHORN_ITERS, thresh=SINKHORN_THRESH, trace=False):
+def sinkhorn(K, u, v, max_iter=SINKHORN_ITERS, thresh=SINKHORN_THRESH, trace=False, force_iters=None):
     """diml.py:42-54.  r, c start at one; r-update then c-update; the stop test is the
     mean of |r - r_prev| over the WHOLE batch, evaluated after both updates (so at least
-    one full iteration always runs).  Returns T (and n_iter, [err per iteration])."""
+    one full iteration always runs).  Returns T (and n_iter, [err per iteration]).
+
+    force_iters=n runs exactly n iterations (no stop test).  The reference's stop sits at
+    the fp32 noise floor (r reaches 1e4..1e6 while the threshold is an absolute 0.1), so two
+    correct fp32 implementations can disagree by one iteration; the parity harness uses this
+    switch to compare plans and scores at EQUAL iteration counts ("n* fragility")."""
     r = torch.ones_like(u)
     c = torch.ones_like(v)
     errs = []
     n_iter = 0
+    if force_iters is not None:
+        max_iter, thresh = int(force_iters), float("-inf")
     for _ in range(max_iter):
         r_prev = r
         r = u / torch.matmul(K, c.unsqueeze(-1)).squeeze(-1)
@@ -74,10 +81,10 @@ def partial_extend(K, u, v, ot_part):
     return Ke, ue, ve
 
 
-def sinkhorn_partial(K, u, v, ot_part=0.1, trace=False):
+def sinkhorn_partial(K, u, v, ot_part=0.1, trace=False, force_iters=None):
     """diml.py:59-75: returns the extended plan [b, m+1, n+1]."""
     Ke, ue, ve = partial_extend(K, u, v, ot_part)
-    return sinkhorn(Ke, ue, ve, trace=trace)
+    return sinkhorn(Ke, ue, ve, trace=trace, force_iters=force_iters)
 
 
 def global_similarity(q_center, centers):
@@ -155,7 +162,7 @@ def select_mode(use_uniform=False, use_inverse=False, use_minus=False, use_soft=
 
 def structural_similarity(anchor, anchor_center, fb, fb_center, mode, ot_temp=0.05,
                           temperature=1.0, use_cls_token=False, ot_part=1.0,
-                          q_rollout=None, c_rollout=None, trace=False):
+                          q_rollout=None, c_rollout=None, trace=False, force_iters=None):
     """Stage 1 of calc_similarity (diml.py:86-147) and of calc_similarity_cvt_rollout
     (:331-366; mode == 'rollout').  Returns score [n], (u, v, T or T_ext, sim_r, cc)
     and, with trace=True, also (n_iter, errs)."""
@@ -173,10 +180,10 @@ def structural_similarity(anchor, anchor_center, fb, fb_center, mode, ot_temp=0.
     u, v, cc = marginals(mode, anchor, anchor_center, fb, fb_center, temperature,
                          q_rollout, c_rollout)
     if ot_part > 0.999:
-        T, n_iter, errs = sinkhorn(K, u, v, trace=True)
+        T, n_iter, errs = sinkhorn(K, u, v, trace=True, force_iters=force_iters)
         T_out = T
     else:
-        T_out, n_iter, errs = sinkhorn_partial(K, u, v, ot_part, trace=True)
+        T_out, n_iter, errs = sinkhorn_partial(K, u, v, ot_part, trace=True, force_iters=force_iters)
         T = T_out[:, :r, :r]
     sim_r = T * sim
     score = torch.sum(sim_r, dim=(1, 2))
@@ -208,7 +215,7 @@ def recall_at(tops, query_label, labels, ks=(1, 2, 4, 8)):
 def evaluate_banks(patches, centers, rollout, labels, trunc_nums=None, use_rollout=False,
                    use_uniform=False, use_inverse=False, temperature=1.0,
                    use_cls_token=False, use_minus=False, ot_part=0.1, query_ids=None,
-                   dump=False):
+                   dump=False, force_iters=None):
     """The per-query loop of eval_cvt_diml.py:308-372 + :402-416 over pre-built banks.
 
     Branch selection follows :201,334-351: with use_rollout the rollout branch runs and
@@ -227,7 +234,7 @@ def evaluate_banks(patches, centers, rollout, labels, trunc_nums=None, use_rollo
     mode = "rollout" if use_rollout else select_mode(use_uniform, use_inverse, use_minus)
     if use_rollout and use_uniform:
         mode = "uniform"
-    for idx in qids:
+    for qpos, idx in enumerate(qids):
         q_center = centers[idx]
         anchor = patches[idx]
         approx = global_similarity(q_center, centers).clone()
@@ -240,7 +247,8 @@ def evaluate_banks(patches, centers, rollout, labels, trunc_nums=None, use_rollo
                 anchor, q_center, patches[top], centers[top], mode, ot_temp=0.05,
                 temperature=temperature, use_cls_token=use_cls_token, ot_part=ot_part,
                 q_rollout=rollout[idx] if rollout is not None else None,
-                c_rollout=rollout[top] if rollout is not None else None, trace=True)
+                c_rollout=rollout[top] if rollout is not None else None, trace=True,
+                force_iters=None if force_iters is None else int(force_iters[qpos]))
             total = score + approx[top]
             rank = torch.argsort(total, descending=True)
             if dump:
