@@ -168,7 +168,7 @@ int vr_stage0_topk(vr_ctx* ctx, const float* q_centers, const int64_t* self_idx,
 
 size_t vr_rerank_workspace_bytes(vr_ctx* ctx, int64_t nq, int32_t k, const vr_ot_params* p) {
     if (!ctx || !p || ctx->n <= 0) return 0;
-    if (pair_fused_supports(ctx->c, ctx->r, k)) return 256;
+    if (pair_fused_supports(ctx->c, ctx->r, k, p)) return 256;
     return generic_rerank_workspace_bytes(nq, k, ctx->r, p);
 }
 
@@ -188,7 +188,7 @@ int vr_rerank_scores(vr_ctx* ctx, int64_t q_start, int64_t q_stride, int64_t nq,
                "rerank: query range outside the gallery");
     VR_CHECK_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
-    if (pair_fused_supports(ctx->c, ctx->r, k)) {
+    if (pair_fused_supports(ctx->c, ctx->r, k, p)) {
         PairArgs a{};
         a.q_patches = ctx->patches;
         a.q_centers = ctx->centers;
@@ -258,7 +258,7 @@ int vr_sinkhorn(const float* K, const float* u, const float* v, int64_t b, int32
 
 size_t vr_calc_similarity_workspace_bytes(int64_t n, int32_t c, int32_t r, const vr_ot_params* p) {
     if (!p) return 0;
-    if (n <= 0x7fffffff && pair_fused_supports(c, r, (int)n)) return 256;
+    if (n <= 0x7fffffff && pair_fused_supports(c, r, (int)n, p)) return 256;
     return generic_rerank_workspace_bytes(1, (int)n, r, p);
 }
 
@@ -278,7 +278,7 @@ int vr_calc_similarity(vr_ctx* ctx, const float* anchor, const float* anchor_cen
     VR_REQUIRE(p->mode != VR_MODE_ROLLOUT || (q_rollout && c_rollout), "calc_similarity: rollout marginals missing");
     VR_CHECK_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
-    if (pair_fused_supports(c, r, (int)n) && ((uintptr_t)anchor & 15) == 0 && ((uintptr_t)fb & 15) == 0) {
+    if (pair_fused_supports(c, r, (int)n, p) && ((uintptr_t)anchor & 15) == 0 && ((uintptr_t)fb & 15) == 0) {
         PairArgs a{};
         a.q_patches = anchor;
         a.q_centers = anchor_center;
@@ -356,7 +356,7 @@ int vr_evaluate_registered(vr_ctx* ctx, int64_t q_start, int64_t q_stride, int64
 
     // chunk the queries so that per-chunk buffers stay bounded
     int64_t chunk = std::min<int64_t>(nq, 16384);
-    const bool fused = k > 0 && pair_fused_supports(ctx->c, ctx->r, k);
+    const bool fused = k > 0 && pair_fused_supports(ctx->c, ctx->r, k, p);
     if (k > 0 && !fused) {
         size_t per_q = generic_rerank_workspace_bytes(1, k, ctx->r, p);
         chunk = std::max<int64_t>(1, std::min<int64_t>(chunk, (int64_t)((size_t)1536 * 1024 * 1024 / per_q)));

@@ -276,41 +276,47 @@ struct IterArgs {
     float thresh;
 };
 
-constexpr int GI_THREADS = 128;
+constexpr int GI_THREADS = 256;
 
+// Same arithmetic order as the reference's CPU bmm (and as pair_fused.cu): every output is one
+// sequential FMA chain over the inner index, followed by an IEEE division.  K is staged in
+// shared memory with a padded row (conflict-free for both passes) when it fits, else read
+// from global memory.
+template <bool STAGED>
 __global__ void __launch_bounds__(GI_THREADS) generic_iter_kernel(IterArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* cs = reinterpret_cast<float*>(smem_raw);  // [cols]
     float* rs = cs + a.cols;                          // [rows]
     float* red = rs + a.rows;                         // [32]
+    float* Ks = red + 32;                             // [rows][cols + 1] when STAGED
     const int64_t pair = blockIdx.x;
     const int64_t qi = pair / a.k;
     if (a.done[qi] || a.e[pair] < 0.f) return;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int rows = a.rows, cols = a.cols;
-    const float* K = a.K + pair * (int64_t)rows * cols;
+    const int tid = threadIdx.x;
+    const int rows = a.rows, cols = a.cols, ld = STAGED ? cols + 1 : cols;
+    const float* Kg = a.K + pair * (int64_t)rows * cols;
     const float* u = a.u + pair * rows;
     const float* v = a.v + pair * cols;
     float* rv = a.rv + pair * rows;
     float* cv = a.cv + pair * cols;
     for (int m = tid; m < cols; m += GI_THREADS) cs[m] = cv[m];
+    if (STAGED)
+        for (int i = tid; i < rows * cols; i += GI_THREADS) Ks[(i / cols) * ld + (i % cols)] = Kg[i];
     __syncthreads();
+    const float* K = STAGED ? Ks : Kg;
     float e = 0.f;
-    for (int s = warp; s < rows; s += GI_THREADS / 32) {
+    for (int s = tid; s < rows; s += GI_THREADS) {
         float y = 0.f;
-        for (int m = lane; m < cols; m += 32) y = fmaf(K[(int64_t)s * cols + m], cs[m], y);
-        y = warp_sum(y);
-        if (lane == 0) {
-            const float rn = u[s] / y;
-            e += fabsf(rn - rv[s]);
-            rv[s] = rn;
-            rs[s] = rn;
-        }
+        for (int m = 0; m < cols; m++) y = fmaf(K[(int64_t)s * ld + m], cs[m], y);
+        const float rn = u[s] / y;
+        e += fabsf(rn - rv[s]);
+        rv[s] = rn;
+        rs[s] = rn;
     }
     __syncthreads();
     for (int m = tid; m < cols; m += GI_THREADS) {
         float x = 0.f;
-        for (int s = 0; s < rows; s++) x = fmaf(K[(int64_t)s * cols + m], rs[s], x);
+        for (int s = 0; s < rows; s++) x = fmaf(K[(int64_t)s * ld + m], rs[s], x);
         cv[m] = v[m] / x;
     }
     e = block_reduce_sum(e, red);
@@ -419,10 +425,19 @@ size_t generic_rerank_workspace_bytes(int64_t nq, int k, int r, const vr_ot_para
 size_t generic_sinkhorn_workspace_bytes(int64_t b, int m, int n) { return carve(nullptr, 1, b, 0, m, n, false).bytes; }
 
 static int run_iterations(const IterArgs& it, int64_t nq, int64_t np, int max_iter, cudaStream_t st) {
-    size_t smem = (size_t)(it.rows + it.cols + 32) * 4;
-    VR_REQUIRE(smem <= 48 * 1024, "sinkhorn: %d x %d too large", it.rows, it.cols);
+    const size_t base = (size_t)(it.rows + it.cols + 32) * 4;
+    const size_t staged = base + (size_t)it.rows * (it.cols + 1) * 4;
+    const bool use_staged = staged <= 200 * 1024;
+    const size_t smem = use_staged ? staged : base;
+    VR_REQUIRE(base <= 48 * 1024, "sinkhorn: %d x %d too large", it.rows, it.cols);
+    if (use_staged && smem > 48 * 1024)
+        VR_CHECK_CUDA(cudaFuncSetAttribute(generic_iter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem));
     for (int i = 0; i < max_iter; i++) {
-        generic_iter_kernel<<<(unsigned)np, GI_THREADS, smem, st>>>(it);
+        if (use_staged)
+            generic_iter_kernel<true><<<(unsigned)np, GI_THREADS, smem, st>>>(it);
+        else
+            generic_iter_kernel<false><<<(unsigned)np, GI_THREADS, smem, st>>>(it);
         VR_LAUNCH_CHECK();
         generic_decide_kernel<<<(unsigned)nq, 256, 0, st>>>(it, i);
         VR_LAUNCH_CHECK();

@@ -58,7 +58,7 @@ int global_similarity(const float* q, const float* centers, int64_t n, int c, fl
 
 // pair_fused.cu
 int pair_fused_max_clusters(int* out);
-bool pair_fused_supports(int c, int r, int k);
+bool pair_fused_supports(int c, int r, int k, const vr_ot_params* p);
 int pair_fused_launch(const PairArgs& a, int64_t nq, cudaStream_t st);
 
 // generic_ot.cu
