@@ -180,6 +180,12 @@ VR_API int vr_evaluate_registered(vr_ctx* ctx, int64_t q_start, int64_t q_stride
                            const vr_ot_params* p, double* tallies_host, int32_t* per_query_niter_host,
                            void* stream);
 
+/* Diagnostics: when buf is non-NULL, vr_rerank_scores / vr_calc_similarity also write the value of
+ * the stop test (batch mean of |r - r_prev|, diml.py:50) of every iteration they run into
+ * buf[query * max_iter + iteration] (device memory, caller-owned, nq * max_iter floats).  NULL turns
+ * it off.  Used by the parity harness to show how close to the 0.1 threshold a stop was. */
+VR_API int vr_debug_err_trace(vr_ctx* ctx, float* buf);
+
 /* Number of kernels this library launched since the last call (resets the counter). */
 VR_API int64_t vr_take_launch_count(void);
 

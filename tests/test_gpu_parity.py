@@ -304,3 +304,19 @@ def test_nan_propagation(eng):
                                            params(mode="rollout"), q_rollout=roll[0], c_rollout=roll[1:])
     assert n_ref == 100 and int(niter) == 100
     assert torch.isnan(ref_score).all() and torch.isnan(score).all()
+
+
+@pytest.mark.parametrize("b,r,sigma", [(100, 49, 0.6), (37, 49, 1.0), (12, 50, 0.6), (9, 196, 0.6)])
+def test_sinkhorn_bit_exact_given_inputs(eng, b, r, sigma):
+    """Given the same K, u, v, the CUDA Sinkhorn reproduces torch's CPU result BIT FOR BIT: same
+    sequential-FMA mat-vecs, IEEE division (utilities/diml.py:47-53), hence the same iteration
+    count.  (End to end the inputs differ in the last bit -- torch's exp() is Intel VML -- see
+    DESIGN.md "n* fragility".)"""
+    g = synth.make_gallery(b + 1, 64, r, classes=2, seed=b * r, sigma=sigma)
+    K = O.gibbs(O.patch_similarity(g.patches[0], g.patches[1:]))
+    u = O._norm_sum(torch.relu(g.rollout[1:]))
+    v = O._norm_sum(torch.relu(g.rollout[0].expand(b, -1)))
+    T_ref, n_ref, errs = O.sinkhorn(K, u, v, trace=True)
+    T, niter = eng.sinkhorn(K, u, v)
+    assert int(niter) == n_ref
+    assert torch.equal(T.cpu(), T_ref)

@@ -127,3 +127,61 @@ def test_query_loop(G, case):
     assert np.array_equal(np.sort(tops, 1), np.sort(g[f"{name}_top"], 1))
     close(np.stack([d["score"].numpy() for d in out["dump"]]), g[f"{name}_score"])
     assert [d["n_iter"] for d in out["dump"]] == g[f"{name}_niter"].tolist()
+
+
+def _torch_sum_order(x, W=8):
+    """Python mirror of csrc/common.cuh::torch_sum_inner_w (ATen SumKernel.cpp order)."""
+    f32 = np.float32
+    n = x.shape[1]
+    if n < 8:
+        W = 1
+    ILP, LEVELS = 4, 4
+    vec_size = n // W
+    size_ilp = vec_size // ILP
+    acc = np.zeros((LEVELS, ILP, x.shape[0], W), dtype=f32)
+    lg = 0
+    while (1 << lg) < size_ilp:
+        lg += 1
+    level_power = max(4, lg // LEVELS)
+    level_step = 1 << level_power
+    level_mask = level_step - 1
+    vec = lambda i: x[:, i * W:(i + 1) * W]
+    i = 0
+    while i + level_step <= size_ilp:
+        for _ in range(level_step):
+            for k in range(ILP):
+                acc[0, k] = acc[0, k] + vec(i * ILP + k)
+            i += 1
+        for j in range(1, LEVELS):
+            acc[j] = acc[j] + acc[j - 1]
+            acc[j - 1] = 0
+            if (i & (level_mask << (j * level_power))) != 0:
+                break
+    while i < size_ilp:
+        for k in range(ILP):
+            acc[0, k] = acc[0, k] + vec(i * ILP + k)
+        i += 1
+    for j in range(1, LEVELS):
+        acc[0] = acc[0] + acc[j]
+    for i in range(size_ilp * ILP, vec_size):
+        acc[0, 0] = acc[0, 0] + vec(i)
+    for k in range(1, ILP):
+        acc[0, 0] = acc[0, 0] + acc[0, k]
+    fin = np.zeros(x.shape[0], dtype=f32)
+    for k in range(vec_size * W, n):
+        fin = fin + x[:, k]
+    for l in range(W):
+        fin = fin + acc[0, 0][:, l]
+    return fin
+
+
+@pytest.mark.parametrize("n", [5, 16, 49, 50, 196, 197, 600, 1100])
+def test_torch_sum_order(n):
+    """The CUDA kernels add the marginal numerators in ATen's CPU order (common.cuh); this pins
+    that order against the installed torch, bit for bit.  If a torch upgrade changes it, the
+    Sinkhorn iteration counts of the CUDA path and of the reference drift apart."""
+    rng = np.random.default_rng(n)
+    x = (np.abs(rng.standard_normal((4000, n))) * rng.random((4000, 1))).astype(np.float32)
+    ref = torch.from_numpy(x).sum(dim=1, keepdim=True).numpy()[:, 0]
+    got = _torch_sum_order(x)
+    assert np.array_equal(got.view(np.int32), ref.view(np.int32))

@@ -40,6 +40,7 @@ struct vr_ctx {
     // arena: named device buffers that only grow
     std::unordered_map<std::string, std::pair<void*, size_t>> arena;
     cudaStream_t own_stream = nullptr;
+    float* dbg_err = nullptr;  // see vr_debug_err_trace
 };
 
 using namespace vr;
@@ -117,6 +118,12 @@ int vr_destroy(vr_ctx* ctx) {
         if (kv.second.first) cudaFree(kv.second.first);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
+    return VR_OK;
+}
+
+int vr_debug_err_trace(vr_ctx* ctx, float* buf) {
+    VR_REQUIRE(ctx, "ctx is null");
+    ctx->dbg_err = buf;
     return VR_OK;
 }
 
@@ -204,6 +211,7 @@ int vr_rerank_scores(vr_ctx* ctx, int64_t q_start, int64_t q_stride, int64_t nq,
         a.p = *p;
         a.out_score = out_score;
         a.out_niter = out_niter;
+        a.dbg_err = ctx->dbg_err;
         return pair_fused_launch(a, nq, st);
     }
     GenArgs g{};
@@ -224,6 +232,7 @@ int vr_rerank_scores(vr_ctx* ctx, int64_t q_start, int64_t q_stride, int64_t nq,
     g.p = *p;
     g.out_score = out_score;
     g.out_niter = out_niter;
+    g.dbg_err = ctx->dbg_err;
     return generic_rerank(g, workspace, workspace_bytes, st);
 }
 
@@ -299,6 +308,7 @@ int vr_calc_similarity(vr_ctx* ctx, const float* anchor, const float* anchor_cen
         a.out_T = T;
         a.out_simr = sim_r;
         a.out_cc = cc;
+        a.dbg_err = ctx->dbg_err;
         return pair_fused_launch(a, 1, st);
     }
     GenArgs g{};
@@ -324,6 +334,7 @@ int vr_calc_similarity(vr_ctx* ctx, const float* anchor, const float* anchor_cen
     g.out_T = T;
     g.out_simr = sim_r;
     g.out_cc = cc;
+    g.dbg_err = ctx->dbg_err;
     return generic_rerank(g, workspace, workspace_bytes, st);
 }
 

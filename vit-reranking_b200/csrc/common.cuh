@@ -100,6 +100,79 @@ __device__ __forceinline__ void warp_bitonic_sort_desc(unsigned long long* a, in
     __syncwarp();
 }
 
+
+// ---- torch's reduction order for `x.sum(dim=-1)` over a contiguous fp32 row -------------------
+// The marginals are u = att / (att.sum() + 1e-5) (utilities/diml.py:110 etc.).  Sinkhorn's late-
+// iteration error is dominated by a drift proportional to |sum(u)/sum(v) - 1|, which lives at the
+// 1e-7 level, so a 1-ulp difference in att.sum() moves the stop test by ~10% ("n*
+// fragility").  These functions therefore add in exactly the order of ATen's CPU sum kernel
+// (aten/src/ATen/native/cpu/SumKernel.cpp: vectorized_inner_sum -> row_sum (ILP 4) ->
+// multi_row_sum (4-level cascade), 8-lane fp32 vectors), verified bit-exact against torch 2.11
+// on 200k random rows (tests/test_oracle_golden.py::test_torch_sum_order pins the formula).
+__device__ __forceinline__ float torch_sum49(const float* x) {
+    // 6 vectors of 8 + 1 tail element: lanes ((x0+x4)+x5) + x1 + x2 + x3, then tail + lanes in order
+    float tot = x[48];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        float p0 = x[j] + x[32 + j];
+        p0 += x[40 + j];
+        p0 += x[8 + j];
+        p0 += x[16 + j];
+        p0 += x[24 + j];
+        tot += p0;
+    }
+    return tot;
+}
+
+// General length (serial; one thread).  W = 8 lanes when n >= 8, else the scalar path (W = 1).
+template <int W>
+__device__ float torch_sum_inner_w(const float* x, int n) {
+    constexpr int ILP = 4, LEVELS = 4;
+    const int vec_size = n / W;
+    const int size_ilp = vec_size / ILP;
+    float acc[LEVELS][ILP][W];
+    for (int a = 0; a < LEVELS; a++)
+        for (int k = 0; k < ILP; k++)
+            for (int l = 0; l < W; l++) acc[a][k][l] = 0.f;
+    int lg = 0;
+    while ((1 << lg) < size_ilp) lg++;  // CeilLog2
+    const int level_power = max(4, lg / LEVELS);
+    const int level_step = 1 << level_power;
+    const int level_mask = level_step - 1;
+    int i = 0;
+    for (; i + level_step <= size_ilp;) {
+        for (int j = 0; j < level_step; ++j, ++i)
+            for (int k = 0; k < ILP; k++)
+                for (int l = 0; l < W; l++) acc[0][k][l] += x[(i * ILP + k) * W + l];
+        for (int j = 1; j < LEVELS; ++j) {
+            for (int k = 0; k < ILP; k++)
+                for (int l = 0; l < W; l++) {
+                    acc[j][k][l] += acc[j - 1][k][l];
+                    acc[j - 1][k][l] = 0.f;
+                }
+            const int mask = level_mask << (j * level_power);
+            if ((i & mask) != 0) break;
+        }
+    }
+    for (; i < size_ilp; ++i)
+        for (int k = 0; k < ILP; k++)
+            for (int l = 0; l < W; l++) acc[0][k][l] += x[(i * ILP + k) * W + l];
+    for (int j = 1; j < LEVELS; ++j)
+        for (int k = 0; k < ILP; k++)
+            for (int l = 0; l < W; l++) acc[0][k][l] += acc[j][k][l];
+    for (i = size_ilp * ILP; i < vec_size; ++i)
+        for (int l = 0; l < W; l++) acc[0][0][l] += x[i * W + l];
+    for (int k = 1; k < ILP; k++)
+        for (int l = 0; l < W; l++) acc[0][0][l] += acc[0][k][l];
+    float fin = 0.f;
+    for (int k = vec_size * W; k < n; ++k) fin += x[k];
+    for (int l = 0; l < W; l++) fin += acc[0][0][l];
+    return fin;
+}
+__device__ __forceinline__ float torch_sum_inner(const float* x, int n) {
+    return n >= 8 ? torch_sum_inner_w<8>(x, n) : torch_sum_inner_w<1>(x, n);
+}
+
 // ---- mbarrier + bulk async copy (TMA 1-D) --------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);

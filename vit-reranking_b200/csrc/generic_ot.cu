@@ -196,11 +196,10 @@ __global__ void __launch_bounds__(GP_THREADS) generic_prepare_kernel(GenArgs a) 
         mu = block_reduce_max(lu, red);
         mv = block_reduce_max(lv, red);
     }
-    float su = 0.f, sv = 0.f;
     for (int s = tid; s < R; s += GP_THREADS) {
         float x, y;
         switch (mode) {
-            case VR_MODE_UNIFORM: x = y = 1.0f / (float)R; break;
+            case VR_MODE_UNIFORM: x = y = (float)(1.0 / (double)R); break;
             case VR_MODE_ROLLOUT:
                 x = fmaxf(a.c_rollout[(int64_t)cand * R + s], 0.f);
                 y = fmaxf(a.q_rollout[qid * R + s], 0.f);
@@ -224,23 +223,27 @@ __global__ void __launch_bounds__(GP_THREADS) generic_prepare_kernel(GenArgs a) 
         }
         uo[s] = x;
         vo[s] = y;
-        su += x;
-        sv += y;
     }
-    su = block_reduce_sum(su, red);
-    sv = block_reduce_sum(sv, red);
+    // row sums in torch's reduction order (common.cuh: torch_sum_inner); one thread each
+    auto row_sums = [&](float& su, float& sv) {
+        __syncthreads();
+        if (tid == 0) red[0] = torch_sum_inner(uo, R);
+        if (tid == 32) red[1] = torch_sum_inner(vo, R);
+        __syncthreads();
+        su = red[0];
+        sv = red[1];
+        __syncthreads();
+    };
+    float su = 0.f, sv = 0.f;
     if (mode == VR_MODE_SOFT) {  // softmax, then the common /(sum + 1e-5)
-        float s2u = 0.f, s2v = 0.f;
+        row_sums(su, sv);
         for (int s = tid; s < R; s += GP_THREADS) {
             uo[s] = uo[s] / su;
             vo[s] = vo[s] / sv;
-            s2u += uo[s];
-            s2v += vo[s];
         }
-        su = block_reduce_sum(s2u, red);
-        sv = block_reduce_sum(s2v, red);
     }
     if (mode != VR_MODE_UNIFORM) {
+        row_sums(su, sv);
         su += 1e-5f;
         sv += 1e-5f;
         for (int s = tid; s < R; s += GP_THREADS) {
@@ -323,7 +326,7 @@ __global__ void __launch_bounds__(GI_THREADS) generic_iter_kernel(IterArgs a) {
     if (tid == 0) a.e[pair] = e;
 }
 
-__global__ void __launch_bounds__(256) generic_decide_kernel(IterArgs a, int it) {
+__global__ void __launch_bounds__(256) generic_decide_kernel(IterArgs a, int it, float* dbg_err, int max_iter) {
     __shared__ float red[32];
     const int64_t qi = blockIdx.x;
     if (a.done[qi]) return;
@@ -333,6 +336,7 @@ __global__ void __launch_bounds__(256) generic_decide_kernel(IterArgs a, int it)
     if (threadIdx.x == 0) {
         a.niter[qi] = it + 1;
         const float mean = s / ((float)a.k * (float)a.rows);
+        if (dbg_err) dbg_err[qi * max_iter + it] = mean;
         if (mean < a.thresh) a.done[qi] = 1;
     }
 }
@@ -424,7 +428,7 @@ size_t generic_rerank_workspace_bytes(int64_t nq, int k, int r, const vr_ot_para
 
 size_t generic_sinkhorn_workspace_bytes(int64_t b, int m, int n) { return carve(nullptr, 1, b, 0, m, n, false).bytes; }
 
-static int run_iterations(const IterArgs& it, int64_t nq, int64_t np, int max_iter, cudaStream_t st) {
+static int run_iterations(const IterArgs& it, int64_t nq, int64_t np, int max_iter, float* dbg_err, cudaStream_t st) {
     const size_t base = (size_t)(it.rows + it.cols + 32) * 4;
     const size_t staged = base + (size_t)it.rows * (it.cols + 1) * 4;
     const bool use_staged = staged <= 200 * 1024;
@@ -439,7 +443,7 @@ static int run_iterations(const IterArgs& it, int64_t nq, int64_t np, int max_it
         else
             generic_iter_kernel<false><<<(unsigned)np, GI_THREADS, smem, st>>>(it);
         VR_LAUNCH_CHECK();
-        generic_decide_kernel<<<(unsigned)nq, 256, 0, st>>>(it, i);
+        generic_decide_kernel<<<(unsigned)nq, 256, 0, st>>>(it, i, dbg_err, max_iter);
         VR_LAUNCH_CHECK();
     }
     return VR_OK;
@@ -465,7 +469,7 @@ int generic_rerank(GenArgs a, void* ws, size_t ws_bytes, cudaStream_t st) {
     generic_prepare_kernel<<<(unsigned)np, GP_THREADS, smem, st>>>(a);
     VR_LAUNCH_CHECK();
     IterArgs it{w.K, w.u, w.v, w.rv, w.cv, w.e, w.done, w.niter, re, re, a.k, a.p.thresh};
-    int rc = run_iterations(it, a.nq, np, a.p.max_iter, st);
+    int rc = run_iterations(it, a.nq, np, a.p.max_iter, a.dbg_err, st);
     if (rc) return rc;
     FinishArgs f{w.K, w.sim, w.rv, w.cv, re, re, a.r, a.out_T, a.out_simr, a.out_score};
     generic_finish_kernel<<<(unsigned)np, 256, 0, st>>>(f);
@@ -489,7 +493,7 @@ int generic_sinkhorn(const float* K, const float* u, const float* v, int64_t b, 
     generic_init_kernel<<<(unsigned)((mx + 255) / 256), 256, 0, st>>>(w.rv, w.cv, w.e, b * m, b * n, b, w.done, w.niter, 1);
     VR_LAUNCH_CHECK();
     IterArgs it{K, u, v, w.rv, w.cv, w.e, w.done, w.niter, m, n, (int)b, thresh};
-    int rc = run_iterations(it, 1, b, max_iter, st);
+    int rc = run_iterations(it, 1, b, max_iter, nullptr, st);
     if (rc) return rc;
     FinishArgs f{K, nullptr, w.rv, w.cv, m, n, 0, T, nullptr, nullptr};
     generic_finish_kernel<<<(unsigned)b, 256, 0, st>>>(f);

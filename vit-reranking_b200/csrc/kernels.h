@@ -19,6 +19,7 @@ struct PairArgs {
     float* out_score;         // [nq, k]
     int32_t* out_niter;       // [nq] or nullptr
     float *out_u, *out_v, *out_T, *out_simr, *out_cc;  // optional, [nq*k, ...]
+    float* dbg_err;           // optional [nq, max_iter]: the stop-test value of every iteration
 };
 
 struct GenArgs {
@@ -47,6 +48,7 @@ struct GenArgs {
     float* out_score;
     int32_t* out_niter;
     float *out_u, *out_v, *out_T, *out_simr, *out_cc;
+    float* dbg_err;
 };
 
 // stage0_topk.cu

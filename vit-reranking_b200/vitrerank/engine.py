@@ -120,6 +120,18 @@ class RerankEngine:
         except Exception:
             pass
 
+    def err_trace(self, nq, max_iter=100):
+        """Diagnostics: returns a [nq, max_iter] device tensor that the next rerank_scores /
+        calc_similarity calls fill with the stop-test value of every iteration (NaN = not run).
+        Call err_trace(0) to switch it off."""
+        if nq <= 0:
+            self._trace = None
+            check(lib.vr_debug_err_trace(self._h, C.c_void_p(0)))
+            return None
+        self._trace = torch.full((nq, max_iter), float('nan'), dtype=torch.float32, device=self.device)
+        check(lib.vr_debug_err_trace(self._h, _ptr(self._trace)))
+        return self._trace
+
     # ---- gallery -----------------------------------------------------------------------
     def register(self, patches, centers, rollout=None, labels=None):
         """patches [N,C,R], centers [N,C], rollout [N,R], labels [N]; moved to the device if
