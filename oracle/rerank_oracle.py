@@ -223,6 +223,12 @@ def evaluate_banks(patches, centers, rollout, labels, trunc_nums=None, use_rollo
     calc_similarity runs with ot_temp=0.05.  The blend is a plain sum (:357).  The
     tallies are divided by N/100 where N is the gallery size (:403-405), also when only a
     subset of queries is evaluated (query_ids) -- callers rescale.
+
+    Ties: the reference calls torch.argsort(descending=True) without stable=True (:329,:357), so
+    the order of candidates with bit-identical scores is implementation-defined (it is neither
+    ascending nor descending by index in practice).  The oracle fixes "lower index first", one
+    admissible outcome and the rule of the CUDA path; the golden fixtures made by the real
+    reference agree on every case that has no exact tie among the first num_pos entries.
     """
     trunc_nums = trunc_nums or [0, 5, 10, 50, 100, 500, 1000]
     n = patches.shape[0]
@@ -239,7 +245,7 @@ def evaluate_banks(patches, centers, rollout, labels, trunc_nums=None, use_rollo
         anchor = patches[idx]
         approx = global_similarity(q_center, centers).clone()
         approx[idx] = SELF_MASK
-        approx_tops = torch.argsort(approx, descending=True)
+        approx_tops = torch.argsort(approx, descending=True, stable=True)   # ties: see docstring
         rec = {"q": idx}
         if kmax > 0:
             top = approx_tops[:kmax]
@@ -250,7 +256,7 @@ def evaluate_banks(patches, centers, rollout, labels, trunc_nums=None, use_rollo
                 c_rollout=rollout[top] if rollout is not None else None, trace=True,
                 force_iters=None if force_iters is None else int(force_iters[qpos]))
             total = score + approx[top]
-            rank = torch.argsort(total, descending=True)
+            rank = torch.argsort(total, descending=True, stable=True)
             if dump:
                 rec.update(top=top.clone(), approx=approx[top].clone(), score=score.clone(),
                            total=total.clone(), rank=rank.clone(), n_iter=n_iter, errs=errs)
