@@ -159,6 +159,12 @@ VR_API int vr_calc_similarity(vr_ctx* ctx, const float* anchor, const float* anc
 VR_API int vr_global_similarity(const float* q_center, const float* centers, int64_t n, int32_t c, float* sim,
                          void* stream);
 
+/* vr_metrics_rank replaces get_metrics_rank(tops, query_label, gallery_label)
+ * (evaluation/metrics.py:26-47) for one ranked list: tops [n_tops] int64 (device), labels [n_labels]
+ * int64 (device); out3 (device, 3 doubles) = r1, R-precision, MAP@R. */
+VR_API int vr_metrics_rank(const int64_t* tops, int64_t n_tops, int64_t query_label, const int64_t* labels,
+                           int64_t n_labels, double* out3, void* stream);
+
 /* Whole pass with HOST buffers (the end-to-end entry) -----------------------------------
  * Replaces the query loop eval_cvt_diml.py:308-372 over host-resident banks, as the
  * reference keeps them (feature_bank and rollout_list live on the CPU, :278,:256): copies

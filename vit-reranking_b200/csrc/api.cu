@@ -343,6 +343,11 @@ int vr_global_similarity(const float* q_center, const float* centers, int64_t n,
     return global_similarity(q_center, centers, n, c, sim, (cudaStream_t)stream);
 }
 
+int vr_metrics_rank(const int64_t* tops, int64_t n_tops, int64_t query_label, const int64_t* labels, int64_t n_labels,
+                    double* out3, void* stream) {
+    return metrics_rank(tops, n_tops, query_label, labels, n_labels, out3, (cudaStream_t)stream);
+}
+
 int vr_evaluate_registered(vr_ctx* ctx, int64_t q_start, int64_t q_stride, int64_t nq, const int32_t* trunc_nums_host,
                            int32_t n_trunc, int32_t max_num_pos, const vr_ot_params* p, double* tallies_host,
                            int32_t* per_query_niter_host, void* stream) {

@@ -121,6 +121,62 @@ __global__ void __launch_bounds__(256) tally_kernel(const double* per_query, int
     if (threadIdx.x == 0) tallies[col] += red[0];
 }
 
+
+// Direct call: evaluation/metrics.py:26-47 for ONE ranked list (tops may be N long; only
+// tops[:num_pos] is read).  out = {r1, rp, mapr}.
+__global__ void __launch_bounds__(256) metrics_rank_kernel(const int64_t* tops, int64_t n_tops, int64_t qlabel,
+                                                           const int64_t* labels, int64_t n_labels, double* out) {
+    __shared__ int red[8];
+    __shared__ int s_np;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int cnt = 0;
+    for (int64_t i = tid; i < n_labels; i += 256) cnt += (labels[i] == qlabel) ? 1 : 0;
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (lane == 0) red[warp] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+        int t = 0;
+        for (int i = 0; i < 8; i++) t += red[i];
+        s_np = t;
+    }
+    __syncthreads();
+    if (warp != 0) return;
+    const int np = s_np;
+    const int64_t upto = min((int64_t)np, n_tops);
+    int cum = 0;
+    double ap = 0.0;
+    bool first = false;
+    for (int64_t base = 0; base < upto; base += 32) {
+        const int64_t j = base + lane;
+        bool hit = false;
+        if (j < upto) {
+            const int64_t src = tops[j];
+            hit = src >= 0 && src < n_labels && labels[src] == qlabel;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (base == 0) first = (m & 1u) != 0;
+        if (hit) {
+            const int c = cum + __popc(m & (0xffffffffu >> (31 - lane)));
+            ap += (double)((float)c / (float)(j + 1));
+        }
+        cum += __popc(m);
+    }
+    for (int o = 16; o > 0; o >>= 1) ap += __shfl_xor_sync(0xffffffffu, ap, o);
+    if (lane == 0) {
+        out[0] = first ? 1.0 : 0.0;
+        out[1] = np > 0 ? (double)((float)cum / (float)np) : 0.0;
+        out[2] = np > 0 ? (double)(float)(ap / (double)np) : 0.0;
+    }
+}
+
+int metrics_rank(const int64_t* tops, int64_t n_tops, int64_t qlabel, const int64_t* labels, int64_t n_labels,
+                 double* out, cudaStream_t st) {
+    VR_REQUIRE(tops && labels && out && n_tops > 0 && n_labels > 0, "metrics_rank: bad arguments");
+    metrics_rank_kernel<<<1, 256, 0, st>>>(tops, n_tops, qlabel, labels, n_labels, out);
+    VR_LAUNCH_CHECK();
+    return VR_OK;
+}
+
 size_t finalize_workspace_bytes(int64_t nq, int n_trunc) {
     return align_up((size_t)nq * n_trunc * FN_METRICS * sizeof(double), 256) + 256;
 }

@@ -77,4 +77,7 @@ int finalize(int64_t q_start, int64_t q_stride, int64_t nq, int k, int kp, const
              const int32_t* truncs, int n_trunc, int32_t* out_rank, double* tallies, void* ws, size_t ws_bytes,
              cudaStream_t st);
 
+int metrics_rank(const int64_t* tops, int64_t n_tops, int64_t qlabel, const int64_t* labels, int64_t n_labels,
+                 double* out, cudaStream_t st);
+
 }  // namespace vr

@@ -1,0 +1,209 @@
+"""Drop-in for the reference's evaluation/eval_cvt_diml.py::evaluate (the entry point of
+test_diml_cvt.py).  Same signature, same printed lines, same returned dict
+{'r1': [...], 'rp': [...], 'mapr': [...]} ordered as trunc_nums.
+
+What changed underneath (reference file:line in brackets):
+  * PHASE A (embedding, [:225-305]) still runs the caller's model batch by batch, but the three
+    banks stay in HBM instead of being parked on the host [:278-279,:256].
+  * PHASE B (the per-query Python loop [:316-372]) is ONE batched pass through
+    libvitrerank.so: first-stage top-K' select, fused gather + patch-sim + Sinkhorn + score,
+    blend / re-sort / metric tallies on the GPU (vitrerank.engine.RerankEngine.evaluate).  With
+    torch.distributed initialised, the queries are sharded over the ranks and the tallies are
+    all-reduced (vitrerank.distributed).
+  * The matplotlib / cv2 heat-map hook [:375-397] is not part of this build (it needs the
+    dataset's images and matplotlib; with --plot_topk 1 it raises in the reference, SURVEY.md
+    section 8b).  Pass `visual_hook=callable(idx, uv)` to receive the `uv` tuple of the queries
+    the reference would have drawn (idx < 1000 and idx % 10 == 0).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from vitrerank import distributed as vdist
+from vitrerank.engine import OTParams, RerankEngine
+
+try:  # progress bars as in the reference, optional
+    from tqdm import tqdm
+except Exception:  # pragma: no cover
+    def tqdm(x, **k):
+        return x
+
+
+# ---- attention rollout (input production for --use_rollout; reference [:54-146]) -------------------
+def resize_attn_map(attn, resize, stage, grid, blk_id=0):
+    """[:54-71]: drop the cls row/column in stage 2, pool both token axes to grid x grid."""
+    if stage == 2:
+        attn = attn[:, 1:, 1:]
+    b, h, w = attn.shape
+    side = int(w ** .5)
+    attn = attn.reshape(b, h, side, side)
+    if attn.size(-1) > grid:
+        attn = resize(attn)
+    attn = attn.reshape(b, h, -1).permute(0, 2, 1)
+    side = int(h ** .5)
+    attn = attn.reshape(b, -1, side, side)
+    if attn.size(-1) > grid:
+        attn = resize(attn)
+    return attn.reshape(b, grid * grid, grid * grid).permute(0, 2, 1)
+
+
+def filter_attention_map(raw_attn, discard_ratio, head_fusion, show_fig=False):
+    """[:74-108]: fuse heads, zero the `discard_ratio` smallest entries.  As in the reference the
+    fancy-index assignment zeroes, in EVERY image of the batch, the union of the coordinates
+    discarded in any image."""
+    h, w = raw_attn.size(-2), raw_attn.size(-1)
+    if head_fusion == 'mean':
+        fused = raw_attn.mean(dim=1)
+    elif head_fusion == 'max':
+        fused = raw_attn.max(dim=1)[0]
+    elif head_fusion == 'min':
+        fused = raw_attn.min(dim=1)[0]
+    else:
+        raise ValueError("head fusion type not supported")
+    flat = fused.reshape(fused.size(0), -1)
+    _, idx = flat.topk(int(flat.size(-1) * discard_ratio), -1, False)
+    iy = (idx / w).long()
+    ix = (idx % w).long()
+    out = flat.reshape(flat.size(0), h, w)
+    out[:, iy, ix] = 0
+    return out
+
+
+def get_attention_rollout(model, input, grid=7, use_res=True, display_map=False):
+    """[:111-146]: per-block attention (blk._probs[0]) -> min-fused, filtered, pooled to
+    grid^2 x grid^2, identity added and row-normalised, then chained with bmm.  Returns the list
+    of joint attentions (one per block); evaluate keeps joint[-1].mean(1)."""
+    with torch.no_grad():
+        model.both_forward(input)
+        resize = nn.AdaptiveAvgPool2d((grid, grid))
+        mats = []
+        for si in range(3):
+            stage = getattr(model, f'stage{si}')
+            for i, blk in enumerate(stage.blocks):
+                a = filter_attention_map(blk._probs[0], discard_ratio=0.1, head_fusion='min')
+                mats.append(resize_attn_map(a, resize, si, grid, blk_id=i).detach())
+        mats = torch.stack(mats)
+        if use_res:
+            eye = torch.eye(mats.size(2), device=mats.device, dtype=mats.dtype)
+            mats = mats + eye
+            mats = mats / mats.sum(dim=-1).unsqueeze(-1)
+    joint = [mats[0]]
+    for j in range(1, len(mats)):
+        joint.append(torch.bmm(mats[j], joint[j - 1]))
+    return joint
+
+
+def evaluate_patch_similarity(model, dataset, dataloader):
+    raise NotImplementedError("evaluate_patch_similarity ([:168-194], ViT block self-similarity statistics) is "
+                              "off the rerank path; not part of the B200 build")
+
+
+# ---- PHASE A: embed the test set into three HBM-resident banks [:225-305] ----------------------------
+def embed_banks(model, dataloader, training=False, grid_size=4, use_rollout=False, device=None):
+    device = device or torch.device('cuda')
+    no_training = not training
+    resize = None
+    if no_training:
+        if 7 % grid_size == 0:
+            resize = nn.AdaptiveAvgPool2d(grid_size)
+        else:
+            resize = nn.Sequential(nn.Upsample(grid_size * 4, mode='bilinear', align_corners=True),
+                                   nn.AdaptiveAvgPool2d(grid_size))
+    banks, centers, labels, rollouts = [], [], [], []
+    with torch.no_grad():
+        for inp in tqdm(dataloader, desc='Embedding Data...'):
+            img, target = inp[1].to(device), inp[0]
+            out = model(img)
+            if use_rollout:
+                rollout = get_attention_rollout(model.model, img, display_map=False)
+                rollouts.append(rollout[-1].mean(1).detach().to(device))
+            aux = None
+            if isinstance(out, tuple):
+                out, aux = out
+            if no_training:
+                _, tokens = aux
+                tokens = model.model.head(tokens).permute(0, 2, 1)           # bs x C x L
+                side = int(tokens.size(-1) ** 0.5)
+                tokens = tokens.reshape(tokens.size(0), -1, side, side)
+                if tokens.size(-1) != grid_size:
+                    tokens = resize(tokens)
+                banks.append(tokens.reshape(tokens.size(0), tokens.size(1), -1).detach())
+                centers.append(out.detach())
+            else:
+                banks.append(out.reshape(out.size(0), out.size(1), -1).detach())
+                centers.append(aux[0].detach())
+            labels.append(torch.as_tensor(target).reshape(-1))
+    bank = torch.nn.functional.normalize(torch.cat(banks, 0).float(), p=2, dim=1)      # [:304]
+    center = torch.nn.functional.normalize(torch.cat(centers, 0).float(), p=2, dim=1)  # [:305]
+    roll = torch.cat(rollouts, 0).float() if use_rollout else None
+    return bank.contiguous(), center.contiguous(), roll, torch.cat(labels, 0).long()
+
+
+def evaluate_banks(patches, centers, rollout, labels, trunc_nums=None, use_uniform=False, use_inverse=False,
+                   temperature=1.0, use_cls_token=False, ot_part=0.1, use_minus=False, use_rollout=False,
+                   device=None, return_extra=False):
+    """PHASE B [:308-372,:402-416] over pre-built banks: the reference's query loop as one batched
+    GPU pass.  Returns the reference's dict (percentages over the N gallery images)."""
+    trunc_nums = trunc_nums or [0, 5, 10, 50, 100, 500, 1000]                   # [:309]
+    if use_rollout and rollout is None and not use_uniform:
+        raise ValueError("use_rollout needs the rollout bank")
+    eng = RerankEngine.get(device if device is not None else (patches.device if patches.is_cuda else None))
+    eng.register(patches, centers, rollout, labels)
+    params = OTParams.from_flags(use_rollout=use_rollout, use_uniform=use_uniform, use_inverse=use_inverse,
+                                 use_minus=use_minus, temperature=temperature, use_cls_token=use_cls_token,
+                                 ot_part=ot_part, ot_temp=0.05)                  # [:341], diml.py:325
+    n = patches.shape[0]
+    tallies, niter = vdist.evaluate_sharded(eng, trunc_nums, params)
+    scale = float(n / 100)                                                       # [:403-405]
+    data = {
+        'r1': [float(tallies[i, 0] / scale) for i in range(len(trunc_nums))],
+        'rp': [float(tallies[i, 1] / scale) for i in range(len(trunc_nums))],
+        'mapr': [float(tallies[i, 2] / scale) for i in range(len(trunc_nums))],
+    }
+    if return_extra:
+        data['recall_at_1_2_4_8'] = [[float(x / scale) for x in tallies[i, 3:7]] for i in range(len(trunc_nums))]
+        data['sinkhorn_iters'] = niter
+    return data
+
+
+def evaluate(model, dataset, dataloader, training=False, trunc_nums=None, use_uniform=False, grid_size=4,
+             use_inverse=False, temperature=1.0, use_cls_token=False, attn_blk_ind=0, use_ot=True, ot_part=0.1,
+             to_submit=False, use_minus=False, use_rollout=False, plot_topk=1, visual_hook=None):
+    """evaluation/eval_cvt_diml.py:196-416."""
+    device = torch.device('cuda')
+    model.eval()
+    patches, centers, rollout, labels = embed_banks(model, dataloader, training=training, grid_size=grid_size,
+                                                    use_rollout=use_rollout, device=device)
+    trunc_nums = trunc_nums or [0, 5, 10, 50, 100, 500, 1000]
+    data = evaluate_banks(patches, centers, rollout, labels, trunc_nums=trunc_nums, use_uniform=use_uniform,
+                          use_inverse=use_inverse, temperature=temperature, use_cls_token=use_cls_token,
+                          ot_part=ot_part, use_minus=use_minus, use_rollout=use_rollout, device=device)
+    if visual_hook is not None and max(trunc_nums) > 0:
+        _run_visual_hook(visual_hook, patches, centers, rollout, max(trunc_nums), use_rollout, use_uniform,
+                         use_inverse, use_minus, temperature, use_cls_token, ot_part)
+    for i, trunc_num in enumerate(trunc_nums):                                   # [:407-409]
+        print(f"trunc_num: {trunc_num}, ot part: {ot_part}")
+        print('###########')
+        print('Now rank-1 acc=%f, RP=%f, MAP@R=%f' % (data['r1'][i], data['rp'][i], data['mapr'][i]))
+    return data
+
+
+def _run_visual_hook(hook, patches, centers, rollout, k, use_rollout, use_uniform, use_inverse, use_minus,
+                     temperature, use_cls_token, ot_part):
+    """Materialise the reference's `uv` tuple (u, v, T, sim_r, cc) only for the queries it would
+    have visualised [:390]: idx < 1000 and idx % 10 == 0."""
+    from utilities.diml import calc_similarity, calc_similarity_cvt_rollout
+    eng = RerankEngine.get(patches.device)
+    n = patches.shape[0]
+    for idx in range(0, min(n, 1000), 10):
+        top, _ = eng.stage0_topk(min(k, n), q_start=idx, q_stride=1, nq=1)
+        top = top[0][top[0] >= 0].long()
+        if use_rollout:
+            _, uv = calc_similarity_cvt_rollout(centers[idx], patches[idx], rollout[idx], centers[top], patches[top],
+                                                rollout[top], stage=1, use_uniform=use_uniform, ot_part=ot_part)
+        else:
+            _, uv = calc_similarity(patches[idx], centers[idx], patches[top], centers[top], stage=1,
+                                    use_uniform=use_uniform, use_inverse=use_inverse, temperature=temperature,
+                                    use_cls_token=use_cls_token, ot_temp=0.05, use_minus=use_minus, ot_part=ot_part)
+        hook(idx, uv)

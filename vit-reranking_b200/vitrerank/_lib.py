@@ -56,6 +56,7 @@ def _load():
                                        P(OTParamsStruct), P(C.c_double), vp]),
         "vr_evaluate_registered": (C.c_int, [vp, i64, i64, i64, P(i32), i32, i32, P(OTParamsStruct),
                                              P(C.c_double), vp, vp]),
+        "vr_metrics_rank": (C.c_int, [vp, i64, i64, vp, i64, vp, vp]),
         "vr_debug_err_trace": (C.c_int, [vp, vp]),
         "vr_take_launch_count": (i64, []),
     }
