@@ -1,0 +1,181 @@
+"""GPU tests of the drop-in call surface (utilities.diml, evaluation.metrics,
+evaluation.eval_cvt_diml.evaluate): called exactly as the reference's callers do, checked against
+the fixtures made by the real reference (tests/golden/) and against the oracle."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import rerank_oracle as O
+from vitrerank import synth
+
+from golden.cases import CALC_CASES
+from test_gpu_parity import rel_err, stop_ok
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DEV = "cuda:0"
+
+
+def cuda(g):
+    return g.to(DEV)
+
+
+@pytest.mark.parametrize("case", CALC_CASES, ids=[c[0] for c in CALC_CASES])
+def test_calc_similarity_dropin_vs_reference_outputs(golden_dir, case):
+    import utilities.diml as D
+    name, seed, k, sigma, kw = case
+    G = np.load(os.path.join(golden_dir, "calc_similarity.npz"))
+    g = cuda(synth.make_gallery(k + 1, 128, 49, classes=2, seed=seed, sigma=sigma))
+    score, uv = D.calc_similarity(g.patches[0], g.centers[0], g.patches[1:], g.centers[1:], stage=1, **kw)
+    assert score.is_cuda and score.shape == (k,)
+    assert len(uv) == 5
+    part = kw.get("ot_part", 1.0) <= 0.999
+    assert uv[2].shape == ((k, 50, 50) if part else (k, 49, 49)) and uv[3].shape == (k, 49, 49)
+    np.testing.assert_allclose(uv[0].cpu(), G[f"{name}_u"], rtol=2e-5, atol=1e-7)
+    np.testing.assert_allclose(uv[1].cpu(), G[f"{name}_v"], rtol=2e-5, atol=1e-7)
+    if f"{name}_cc" in G.files:
+        np.testing.assert_allclose(uv[4].cpu(), G[f"{name}_cc"], rtol=1e-5, atol=2e-6)
+    else:
+        assert uv[4] is None
+    # iteration count: recompute the oracle's trace to judge a possible off-by-one
+    mode = O.select_mode(kw.get("use_uniform", False), kw.get("use_inverse", False), kw.get("use_minus", False),
+                         kw.get("use_soft", False))
+    gc = g.to("cpu")
+    _, ruv, (n_ref, errs) = O.structural_similarity(gc.patches[0], gc.centers[0], gc.patches[1:], gc.centers[1:], mode,
+                                                    ot_temp=kw.get("ot_temp", 0.05),
+                                                    temperature=kw.get("temperature", 1.0),
+                                                    use_cls_token=kw.get("use_cls_token", False),
+                                                    ot_part=kw.get("ot_part", 1.0), trace=True)
+    assert n_ref == int(G[f"{name}_meta"][3])
+    close_T = np.allclose(uv[2].cpu().numpy(), G[f"{name}_T"], rtol=2e-4, atol=1e-9)
+    if not close_T:   # one iteration off at a borderline stop: compare at equal counts instead
+        ok = False
+        for n_try in (n_ref - 1, n_ref + 1):
+            if n_try >= 1 and stop_ok(n_try, n_ref, errs):
+                s2, uv2, _ = O.structural_similarity(gc.patches[0], gc.centers[0], gc.patches[1:], gc.centers[1:], mode,
+                                                     ot_temp=kw.get("ot_temp", 0.05),
+                                                     temperature=kw.get("temperature", 1.0),
+                                                     use_cls_token=kw.get("use_cls_token", False),
+                                                     ot_part=kw.get("ot_part", 1.0), trace=True, force_iters=n_try)
+                if np.allclose(uv[2].cpu().numpy(), uv2[2].numpy(), rtol=2e-4, atol=1e-9):
+                    assert rel_err(score.cpu(), s2).max() < 1e-4
+                    ok = True
+        assert ok, "plan differs from the reference beyond a borderline stop"
+    else:
+        assert rel_err(score.cpu(), G[f"{name}_score"]).max() < 1e-4
+        np.testing.assert_allclose(uv[3].cpu(), G[f"{name}_simr"], rtol=2e-4, atol=1e-8)
+
+
+def test_stage0_and_rollout_dropin(golden_dir):
+    import utilities.diml as D
+    G = np.load(os.path.join(golden_dir, "calc_similarity.npz"))
+    seed, k = [int(x) for x in G["stage0_meta"]]
+    g = cuda(synth.make_gallery(k + 1, 128, 49, classes=2, seed=seed, sigma=0.6))
+    sim, none = D.calc_similarity(None, g.centers[0], None, g.centers, 0)
+    assert none is None
+    np.testing.assert_allclose(sim.cpu(), G["stage0_sim"], rtol=0, atol=2e-6)
+    sim2, _ = D.calc_similarity_cvt_rollout(g.centers[0], None, None, g.centers, None, None, 0)
+    assert torch.equal(sim, sim2)
+    seed, k, sigma, n_ref = [int(x) for x in G["rollout_meta"]]
+    g = cuda(synth.make_gallery(k + 1, 128, 49, classes=2, seed=seed, sigma=sigma / 1000))
+    score, uv = D.calc_similarity_cvt_rollout(g.centers[0], g.patches[0], g.rollout[0], g.centers[1:], g.patches[1:],
+                                              g.rollout[1:], stage=1)
+    assert torch.equal(uv[0].cpu(), torch.from_numpy(G["rollout_u"]))      # marginals are bit-exact
+    assert torch.equal(uv[1].cpu(), torch.from_numpy(G["rollout_v"]))
+    if np.allclose(uv[2].cpu().numpy(), G["rollout_T"], rtol=2e-4, atol=1e-9):
+        assert rel_err(score.cpu(), G["rollout_score"]).max() < 1e-4
+    with pytest.raises(NotImplementedError):
+        D.calc_similarity_cvt(g.centers[0], g.patches[0], None, g.centers[1:], g.patches[1:], None, stage=1)
+
+
+def test_sinkhorn_dropin_vs_reference_outputs(golden_dir):
+    import utilities.diml as D
+    G = np.load(os.path.join(golden_dir, "sinkhorn.npz"))
+    for name in ("a", "b", "c"):
+        seed, b, c, r, sigma, n_ref = [int(x) for x in G[f"{name}_meta"]]
+        g = synth.make_gallery(b + 1, c, r, classes=2, seed=seed, sigma=sigma / 1000)
+        K = O.gibbs(O.patch_similarity(g.patches[0], g.patches[1:]))
+        u = g.rollout[1:] / (g.rollout[1:].sum(1, keepdim=True) + 1e-5)
+        v = (g.rollout[0:1] / (g.rollout[0:1].sum(1, keepdim=True) + 1e-5)).expand(b, -1).contiguous()
+        T = D.Sinkhorn(K.to(DEV), u.to(DEV), v.to(DEV))
+        assert torch.equal(T.cpu(), torch.from_numpy(G[f"{name}_T"])), "Sinkhorn must be bit-exact given its inputs"
+        Te = D.Sinkhorn_partial(K.to(DEV), u.to(DEV), v.to(DEV), ot_part=0.5)
+        assert Te.shape == (b, r + 1, r + 1)
+        assert torch.equal(Te.cpu(), torch.from_numpy(G[f"{name}_Tpartial"]))
+
+
+def test_metrics_dropin_vs_reference_outputs(golden_dir):
+    from evaluation.metrics import get_metrics, get_metrics_rank
+    G = np.load(os.path.join(golden_dir, "metrics.npz"))
+    labels = torch.from_numpy(G["labels"])
+    for row, tops in zip(G["rows"], G["tops"]):
+        q = int(row[0])
+        r1, rp, mapr = get_metrics_rank(torch.from_numpy(tops), labels[q], labels)
+        assert r1 == row[1] and abs(rp - row[2]) < 1e-7 and abs(mapr - row[3]) < 1e-6
+    sim = torch.randn(300, generator=torch.Generator().manual_seed(0))
+    a = get_metrics(sim, labels[5], labels)
+    b = O.metrics_rank(torch.argsort(sim, descending=True, stable=True), labels[5], labels)
+    assert a[0] == b[0] and abs(a[1] - b[1]) < 1e-7 and abs(a[2] - b[2]) < 1e-6
+
+
+class _Loader:
+    """Minimal stand-in for the DataLoader of test_diml_cvt.py:80 (no worker processes)."""
+
+    def __init__(self, ds, bs):
+        self.ds, self.bs = ds, bs
+
+    def __iter__(self):
+        for lo in range(0, len(self.ds), self.bs):
+            items = [self.ds[i] for i in range(lo, min(len(self.ds), lo + self.bs))]
+            yield torch.tensor([it[0] for it in items]), torch.stack([it[1] for it in items]), \
+                torch.tensor([it[2] for it in items])
+
+    def __len__(self):
+        return (len(self.ds) + self.bs - 1) // self.bs
+
+
+@pytest.mark.parametrize("flags", [dict(use_rollout=True, use_inverse=True, temperature=0.1, use_ot=True, ot_part=1.0),
+                                   dict(use_inverse=True, temperature=0.1, use_cls_token=True, ot_part=1.0)])
+def test_evaluate_entry_point_with_stub_model(flags, capsys):
+    """evaluate(model, dataset, dataloader, ...) as test_diml_cvt.py:138-151 calls it (north-star flags),
+    on the shim dataset / CvT stub; checked against the oracle run on the very banks it embedded."""
+    sys.path.insert(0, os.path.join(ROOT, "vit-reranking_b200", "shims", "override"))
+    try:
+        import importlib
+        archs = importlib.import_module("architectures")
+        dsets = importlib.import_module("datasets")
+    finally:
+        sys.path.pop(0)
+    import evaluation.eval_cvt_diml as E
+
+    class Opt:
+        arch, embed_dim, seed, dataset, not_pretrained = "cvt_13_normalize", 128, 0, "cub200", True
+    os.environ["VITRERANK_SHIM_N"] = "160"
+    ds = dsets.select("cub200", Opt(), "/tmp")["testing"]
+    model = archs.select(Opt.arch, Opt()).to(DEV)
+    loader = _Loader(ds, 16)
+    truncs = [0, 100]
+    data = E.evaluate(model, ds, loader, False, truncs, grid_size=7, plot_topk=1, **flags)
+    out = capsys.readouterr().out
+    assert "Now rank-1 acc=" in out and "trunc_num: 100, ot part: 1.0" in out
+    assert set(data) == {"r1", "rp", "mapr"} and all(len(v) == 2 for v in data.values())
+    # oracle on the same banks
+    patches, centers, rollout, labels = E.embed_banks(model.eval(), loader, grid_size=7,
+                                                      use_rollout=flags.get("use_rollout", False), device=DEV)
+    assert patches.shape == (160, 128, 49)
+    oflags = dict(use_rollout=flags.get("use_rollout", False), use_inverse=flags.get("use_inverse", False),
+                  temperature=flags["temperature"], use_cls_token=flags.get("use_cls_token", False),
+                  ot_part=flags["ot_part"])
+    extra = E.evaluate_banks(patches, centers, rollout, labels, trunc_nums=truncs, return_extra=True, **oflags)
+    nit = extra["sinkhorn_iters"]
+    cpu = [t.cpu() if t is not None else None for t in (patches, centers, rollout, labels)]
+    ref = O.evaluate_banks(*cpu, trunc_nums=truncs, dump=True, **oflags)
+    for q, d in enumerate(ref["dump"]):
+        assert abs(int(nit[q]) - d["n_iter"]) <= 1
+    if any(int(nit[q]) != d["n_iter"] for q, d in enumerate(ref["dump"])):
+        ref = O.evaluate_banks(*cpu, trunc_nums=truncs, force_iters=nit, **oflags)
+    for key in ("r1", "rp", "mapr"):
+        np.testing.assert_allclose(data[key], ref[key], rtol=1e-6, atol=1e-6)
