@@ -101,10 +101,15 @@ def test_sinkhorn_dropin_vs_reference_outputs(golden_dir):
         u = g.rollout[1:] / (g.rollout[1:].sum(1, keepdim=True) + 1e-5)
         v = (g.rollout[0:1] / (g.rollout[0:1].sum(1, keepdim=True) + 1e-5)).expand(b, -1).contiguous()
         T = D.Sinkhorn(K.to(DEV), u.to(DEV), v.to(DEV))
-        assert torch.equal(T.cpu(), torch.from_numpy(G[f"{name}_T"])), "Sinkhorn must be bit-exact given its inputs"
+        # bit-exact against torch on THIS host given the same K, u, v (K itself may differ in the last bit
+        # from the host the fixture was made on: torch's exp is Intel VML, CPU-dispatched)
+        assert torch.equal(T.cpu(), O.sinkhorn(K, u, v)), "Sinkhorn must be bit-exact given its inputs"
         Te = D.Sinkhorn_partial(K.to(DEV), u.to(DEV), v.to(DEV), ot_part=0.5)
         assert Te.shape == (b, r + 1, r + 1)
-        assert torch.equal(Te.cpu(), torch.from_numpy(G[f"{name}_Tpartial"]))
+        assert torch.equal(Te.cpu(), O.sinkhorn_partial(K, u, v, 0.5))
+        _, n_here, _ = O.sinkhorn(K, u, v, trace=True)
+        if n_here == n_ref:   # same iteration count as on the fixture's host: plans agree to rounding
+            np.testing.assert_allclose(T.cpu(), G[f"{name}_T"], rtol=2e-4, atol=1e-10)
 
 
 def test_metrics_dropin_vs_reference_outputs(golden_dir):
