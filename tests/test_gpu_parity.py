@@ -306,7 +306,7 @@ def test_nan_propagation(eng):
     assert torch.isnan(ref_score).all() and torch.isnan(score).all()
 
 
-@pytest.mark.parametrize("b,r,sigma", [(100, 49, 0.6), (37, 49, 1.0), (12, 50, 0.6), (9, 196, 0.6)])
+@pytest.mark.parametrize("b,r,sigma", [(100, 49, 0.6), (37, 49, 1.0), (12, 50, 0.6), (9, 196, 0.6), (7, 16, 0.6), (5, 10, 1.0)])
 def test_sinkhorn_bit_exact_given_inputs(eng, b, r, sigma):
     """Given the same K, u, v, the CUDA Sinkhorn reproduces torch's CPU result BIT FOR BIT: same
     sequential-FMA mat-vecs, IEEE division (utilities/diml.py:47-53), hence the same iteration

@@ -307,10 +307,17 @@ __global__ void __launch_bounds__(GI_THREADS) generic_iter_kernel(IterArgs a) {
         for (int i = tid; i < rows * cols; i += GI_THREADS) Ks[(i / cols) * ld + (i % cols)] = Kg[i];
     __syncthreads();
     const float* K = STAGED ? Ks : Kg;
+    // torch.bmm switches to a plain (unfused multiply, then add) loop below 400 multiply-adds per
+    // matrix (aten/src/ATen/native/LinearAlgebra.cpp, bmm_out_or_baddbmm_); follow it so that the
+    // result stays bit-identical for tiny problems too.
+    const bool fused = (int64_t)rows * cols >= 400;
     float e = 0.f;
     for (int s = tid; s < rows; s += GI_THREADS) {
         float y = 0.f;
-        for (int m = 0; m < cols; m++) y = fmaf(K[(int64_t)s * ld + m], cs[m], y);
+        if (fused)
+            for (int m = 0; m < cols; m++) y = fmaf(K[(int64_t)s * ld + m], cs[m], y);
+        else
+            for (int m = 0; m < cols; m++) y = __fadd_rn(y, __fmul_rn(K[(int64_t)s * ld + m], cs[m]));
         const float rn = u[s] / y;
         e += fabsf(rn - rv[s]);
         rv[s] = rn;
@@ -319,7 +326,10 @@ __global__ void __launch_bounds__(GI_THREADS) generic_iter_kernel(IterArgs a) {
     __syncthreads();
     for (int m = tid; m < cols; m += GI_THREADS) {
         float x = 0.f;
-        for (int s = 0; s < rows; s++) x = fmaf(K[(int64_t)s * ld + m], rs[s], x);
+        if (fused)
+            for (int s = 0; s < rows; s++) x = fmaf(K[(int64_t)s * ld + m], rs[s], x);
+        else
+            for (int s = 0; s < rows; s++) x = __fadd_rn(x, __fmul_rn(K[(int64_t)s * ld + m], rs[s]));
         cv[m] = v[m] / x;
     }
     e = block_reduce_sum(e, red);
