@@ -20,7 +20,13 @@ kp = max(k, eng.bank["max_num_pos"], 8)
 p = OTParams(mode=mode, use_cls_token=True, temperature=0.1)
 for _ in range(reps):
     idx, approx = eng.stage0_topk(kp)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     score, niter = eng.rerank_scores(idx, k, p)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print(f"rerank_scores: {ms:.3f} ms, {n * k / ms / 1e3:.2f} M pairs/s, {ms * 1e3 / n:.2f} us/query")
     tal, _ = eng.finalize(idx, approx, score, k, [0, k])
 torch.cuda.synchronize()
 print("n", n, "k", k, "niter mean", niter.float().mean().item(), "tallies", (tal[:, :3] / (n / 100)).tolist())

@@ -20,6 +20,7 @@ struct PairArgs {
     int32_t* out_niter;       // [nq] or nullptr
     float *out_u, *out_v, *out_T, *out_simr, *out_cc;  // optional, [nq*k, ...]
     float* dbg_err;           // optional [nq, max_iter]: the stop-test value of every iteration
+    long long* dbg_clk;       // optional [nq, 16]: phase clocks (only read by builds with -DPR_TIMING)
 };
 
 struct GenArgs {
