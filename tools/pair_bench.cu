@@ -109,6 +109,11 @@ int main(int argc, char** argv) {
     double it3[3] = {0};
     for (int q = 0; q < nq; q++)
         for (int i = 0; i < 3; i++) it3[i] += (double)(clk[q * 16 + 9 + i] - clk[q * 16 + 8 + i]);
+    double s3[5] = {0};
+    for (int q = 0; q < nq; q++)
+        for (int i = 0; i < 5; i++) s3[i] += (double)clk[q * 16 + 10 + i];
+    printf("  S3 per chunk (thread 0): wait TMA %.0f, load+split %.0f, wait MMA %.0f, stores+barrier %.0f, issue %.0f cycles\n", s3[0] / nq / 16,
+           s3[1] / nq / 16, s3[2] / nq / 16, s3[3] / nq / 16, s3[4] / nq / 16);
     printf("  iteration 2 of warp 0: %.0f cycles\n", it3[0] / nq);
     printf("  loop per iteration: %.0f cycles; whole CTA after setup: %.0f cycles\n", ph[4] / nq / mi, tot / nq);
 #endif
