@@ -114,7 +114,9 @@ int main(int argc, char** argv) {
         for (int i = 0; i < 5; i++) s3[i] += (double)clk[q * 16 + 10 + i];
     printf("  S3 per chunk (thread 0): wait TMA %.0f, load+split %.0f, wait MMA %.0f, stores+barrier %.0f, issue %.0f cycles\n", s3[0] / nq / 16,
            s3[1] / nq / 16, s3[2] / nq / 16, s3[3] / nq / 16, s3[4] / nq / 16);
-    printf("  iteration 2 of warp 0: %.0f cycles\n", it3[0] / nq);
+    double wc = 0, wn = 0;
+    for (int q = 0; q < nq; q++) { wc += (double)clk[q * 16 + 9]; wn += (double)clk[q * 16 + 15]; }
+    printf("  barrier test of thread 0: %.0f cycles per iteration, found incomplete in %.1f%% of the iterations\n", wc / nq / mi, 100 * wn / nq / mi);
     printf("  loop per iteration: %.0f cycles; whole CTA after setup: %.0f cycles\n", ph[4] / nq / mi, tot / nq);
 #endif
     return 0;
