@@ -21,6 +21,7 @@ struct PairArgs {
     float *out_u, *out_v, *out_T, *out_simr, *out_cc;  // optional, [nq*k, ...]
     float* dbg_err;           // optional [nq, max_iter]: the stop-test value of every iteration
     long long* dbg_clk;       // optional [nq, 16]: phase clocks (only read by builds with -DPR_TIMING)
+    unsigned long long* ex_part;   // exchange buffer of the global transport (set by pair_fused_launch)
 };
 
 struct GenArgs {
