@@ -40,7 +40,7 @@ struct Stage0Args {
 };
 
 template <int BM, int TY, int TX>
-__global__ void __launch_bounds__(S0_THREADS, 1) stage0_select_kernel(Stage0Args a) {
+__global__ void __launch_bounds__(S0_THREADS, 2) stage0_select_kernel(Stage0Args a) {
     constexpr int RM = BM / TY;
     constexpr int CN = S0_BN / TX;
     static_assert(TY * TX == S0_THREADS, "thread grid");
@@ -253,8 +253,10 @@ struct Stage0Plan {
 static Stage0Plan plan_stage0(int64_t nq, int64_t n, int kp, int sms) {
     Stage0Plan pl{};
     pl.P = next_pow2(kp + S0_BN);
-    // largest row block whose candidate buffers fit beside the operand tiles
-    const size_t budget = 200 * 1024;
+    // largest row block whose candidate buffers fit beside the operand tiles with two CTAs per SM.  The gallery is
+    // split (below) only when the row blocks alone cannot fill the SMs: every split starts its threshold from zero and
+    // pays the full series of buffer sorts again, and the sorts, not the FMAs, dominate this kernel.
+    const size_t budget = 110 * 1024;
     pl.bm = 64;
     for (;;) {
         size_t ops = (size_t)2 * (pl.bm + S0_BN) * S0_LD * 4;
@@ -266,7 +268,7 @@ static Stage0Plan plan_stage0(int64_t nq, int64_t n, int kp, int sms) {
     int64_t row_blocks = (nq + pl.bm - 1) / pl.bm;
     int64_t tiles = (n + S0_BN - 1) / S0_BN;
     int ns = 1;
-    if (row_blocks < 2 * (int64_t)sms) ns = (int)((2 * (int64_t)sms + row_blocks - 1) / row_blocks);
+    if (row_blocks < (int64_t)sms) ns = (int)(((int64_t)sms + row_blocks - 1) / row_blocks);
     if (ns > 8) ns = 8;
     if (ns > tiles / 4) ns = (int)(tiles / 4);
     if (ns < 1) ns = 1;
