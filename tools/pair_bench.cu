@@ -116,7 +116,7 @@ int main(int argc, char** argv) {
            s3[1] / nq / 16, s3[2] / nq / 16, s3[3] / nq / 16, s3[4] / nq / 16);
     double wc = 0, wn = 0;
     for (int q = 0; q < nq; q++) { wc += (double)clk[q * 16 + 9]; wn += (double)clk[q * 16 + 15]; }
-    printf("  barrier test of thread 0: %.0f cycles per iteration, found incomplete in %.1f%% of the iterations\n", wc / nq / mi, 100 * wn / nq / mi);
+    printf("  exchange re-polls of thread 0 per query: %.1f in steps 0..3, %.1f later\n", wc / nq, wn / nq);
     printf("  loop per iteration: %.0f cycles; whole CTA after setup: %.0f cycles\n", ph[4] / nq / mi, tot / nq);
 #endif
     return 0;
