@@ -198,7 +198,7 @@ def test_golden_sinkhorn(eng, golden_dir, name):
                                            (96, 196, 6, "minus", dict(use_cls_token=False, ot_part=0.5)),
                                            (128, 49, 12, "rollout", {})])
 def test_generic_path(eng, c, r, k, mode, kw):
-    """Shapes the fused kernel does not cover (and one it does, forced through here by K > 104 or
+    """Shapes the fused kernel does not cover (and one it does, forced through here by K > 112 or
     another R/C) run the workspace-based path; same gates."""
     g = synth.make_gallery(k + 1, c, r, classes=3, seed=7 * k + r, sigma=0.6)
     ref_score, ref_uv, (n_ref, errs) = _oracle_pair(g, mode, **kw)
@@ -218,7 +218,7 @@ EVAL_CASES = [
     (256, 10, 42, 0.8, [0, 10, 50], dict(use_inverse=True, temperature=0.1, use_cls_token=True, ot_part=1.0)),
     (200, 8, 43, 0.6, [0, 20], dict(use_minus=True, ot_part=0.5)),
     (60, 4, 44, 0.6, [0, 100], dict(use_rollout=True, ot_part=1.0)),      # gallery smaller than K
-    (300, 6, 45, 0.6, [0, 120], dict(use_rollout=True, ot_part=1.0)),     # K > 104: workspace path
+    (300, 6, 45, 0.6, [0, 120], dict(use_rollout=True, ot_part=1.0)),     # K > 112: workspace path
 ]
 
 
