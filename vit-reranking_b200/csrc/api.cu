@@ -41,6 +41,7 @@ struct vr_ctx {
     std::unordered_map<std::string, std::pair<void*, size_t>> arena;
     cudaStream_t own_stream = nullptr;
     float* dbg_err = nullptr;  // see vr_debug_err_trace
+    bool packed_valid = false; // the fp16 re-pack of `patches` (arena "packed") matches the registered bank
 };
 
 using namespace vr;
@@ -148,6 +149,7 @@ int vr_bank_register(vr_ctx* ctx, const float* patches, const float* centers, co
     ctx->n = n;
     ctx->c = c;
     ctx->r = r;
+    ctx->packed_valid = false;   // re-packed lazily by the first fused rerank on that call's stream
     return VR_OK;
 }
 
@@ -212,6 +214,16 @@ int vr_rerank_scores(vr_ctx* ctx, int64_t q_start, int64_t q_stride, int64_t nq,
         a.out_score = out_score;
         a.out_niter = out_niter;
         a.dbg_err = ctx->dbg_err;
+        // one-time re-pack of the registered bank into the fp16 operand planes of S3 (a registered bank must not be
+        // modified in place without registering it again)
+        void* packed = nullptr;
+        if ((rc = arena_get(ctx, "packed", pair_fused_packed_bytes(ctx->n), &packed))) return rc;
+        if (!ctx->packed_valid) {
+            if ((rc = pair_fused_repack(ctx->patches, ctx->n, packed, st))) return rc;
+            ctx->packed_valid = true;
+        }
+        a.c_packed_a = packed;
+        a.q_packed_b = (const char*)packed + pair_fused_packed_bytes(ctx->n) / 2;
         return pair_fused_launch(a, nq, st);
     }
     GenArgs g{};
