@@ -320,3 +320,41 @@ def test_sinkhorn_bit_exact_given_inputs(eng, b, r, sigma):
     T, niter = eng.sinkhorn(K, u, v)
     assert int(niter) == n_ref
     assert torch.equal(T.cpu(), T_ref)
+
+
+@pytest.mark.parametrize("mode,kw", [("rollout", {}), ("inverse", dict(temperature=0.1, use_cls_token=True)),
+                                     ("minus", dict(use_cls_token=False))])
+def test_packed_bank_path_equals_direct_path(eng, mode, kw):
+    """A registered bank is re-packed once into fp16 hi / lo operand planes and S3 is fed by TMA; direct calls with
+    unregistered tensors split the fp32 rows on the fly.  Both feed the tensor cores the same bits, so scores and
+    iteration counts must be identical, not just close."""
+    n, k = 150, 100
+    g = synth.make_gallery(n, 128, 49, classes=5, seed=31, sigma=0.6)
+    eng.register(g.patches, g.centers, g.rollout, g.labels)
+    idx, _ = eng.stage0_topk(k)
+    p = params(mode=mode, **kw)
+    score, niter = eng.rerank_scores(idx, k, p)
+    idx_c = idx.cpu().long()
+    for q in (0, 7, 149):
+        s2, _, n2 = eng.calc_similarity(g.patches[q], g.centers[q], g.patches[idx_c[q]], g.centers[idx_c[q]], p,
+                                        q_rollout=g.rollout[q], c_rollout=g.rollout[idx_c[q]], want_uv=False)
+        assert int(n2) == int(niter[q])
+        assert torch.equal(s2.cpu(), score[q].cpu())
+
+
+def test_exchange_transports_agree(eng, monkeypatch):
+    """VR_PAIR_TRANSPORT=cluster (DSMEM, st.async) and the default global transport (tagged words in L2) run the same
+    protocol: identical scores and iteration counts."""
+    n, k = 120, 100
+    g = synth.make_gallery(n, 128, 49, classes=4, seed=32, sigma=0.8)
+    eng.register(g.patches, g.centers, g.rollout, g.labels)
+    idx, _ = eng.stage0_topk(k)
+    p = params(mode="rollout")
+    monkeypatch.delenv("VR_PAIR_TRANSPORT", raising=False)
+    s_g, n_g = eng.rerank_scores(idx, k, p)
+    torch.cuda.synchronize()
+    monkeypatch.setenv("VR_PAIR_TRANSPORT", "cluster")
+    s_c, n_c = eng.rerank_scores(idx, k, p)
+    torch.cuda.synchronize()
+    assert torch.equal(n_g.cpu(), n_c.cpu())
+    assert torch.equal(s_g.cpu(), s_c.cpu())
