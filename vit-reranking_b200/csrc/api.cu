@@ -40,6 +40,9 @@ struct vr_ctx {
     // arena: named device buffers that only grow
     std::unordered_map<std::string, std::pair<void*, size_t>> arena;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // uploads the patch bank while stage 0 runs (vr_evaluate_host)
+    cudaEvent_t patches_ready = nullptr;  // recorded on copy_stream; non-null pending_wait makes the next rerank wait for it
+    bool pending_wait = false;
     float* dbg_err = nullptr;  // see vr_debug_err_trace
     bool packed_valid = false; // the fp16 re-pack of `patches` (arena "packed") matches the registered bank
 };
@@ -102,7 +105,11 @@ int vr_create(int device, vr_ctx** out) {
         return rc;
     }
     ctx->max_clusters = mc;
-    rc = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess ? VR_OK : VR_E_CUDA;
+    rc = (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
+          cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+          cudaEventCreateWithFlags(&ctx->patches_ready, cudaEventDisableTiming) == cudaSuccess)
+             ? VR_OK
+             : VR_E_CUDA;
     if (rc) {
         set_error("vr_create: cudaStreamCreate failed");
         delete ctx;
@@ -118,6 +125,8 @@ int vr_destroy(vr_ctx* ctx) {
     for (auto& kv : ctx->arena)
         if (kv.second.first) cudaFree(kv.second.first);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->patches_ready) cudaEventDestroy(ctx->patches_ready);
     delete ctx;
     return VR_OK;
 }
@@ -197,6 +206,10 @@ int vr_rerank_scores(vr_ctx* ctx, int64_t q_start, int64_t q_stride, int64_t nq,
                "rerank: query range outside the gallery");
     VR_CHECK_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
+    if (ctx->pending_wait) {   // vr_evaluate_host: the patch bank is still being uploaded on the copy stream
+        VR_CHECK_CUDA(cudaStreamWaitEvent(st, ctx->patches_ready, 0));
+        ctx->pending_wait = false;
+    }
     if (pair_fused_supports(ctx->c, ctx->r, k, p)) {
         PairArgs a{};
         a.q_patches = ctx->patches;
@@ -443,8 +456,10 @@ int vr_evaluate_host(vr_ctx* ctx, const float* patches_host, const float* center
     if (rollout_host && (rc = arena_get(ctx, "h_rollout", br, &d_r))) return rc;
     if ((rc = arena_get(ctx, "h_labels", (size_t)n * 8, &d_l))) return rc;
     if ((rc = arena_get(ctx, "h_numpos", (size_t)n * 4, &d_np))) return rc;
-    VR_CHECK_CUDA(cudaMemcpyAsync(d_p, patches_host, bp, cudaMemcpyHostToDevice, st));
+    // the big copy goes on its own stream: stage 0 needs the centres only and runs while the patches are in flight
     VR_CHECK_CUDA(cudaMemcpyAsync(d_c, centers_host, bc, cudaMemcpyHostToDevice, st));
+    VR_CHECK_CUDA(cudaMemcpyAsync(d_p, patches_host, bp, cudaMemcpyHostToDevice, ctx->copy_stream));
+    VR_CHECK_CUDA(cudaEventRecord(ctx->patches_ready, ctx->copy_stream));
     if (rollout_host) VR_CHECK_CUDA(cudaMemcpyAsync(d_r, rollout_host, br, cudaMemcpyHostToDevice, st));
     VR_CHECK_CUDA(cudaMemcpyAsync(d_l, labels_host, (size_t)n * 8, cudaMemcpyHostToDevice, st));
     // num_pos[i] = #{j : label[j] == label[i]}  (metrics.py:34), computed while the copies fly
@@ -462,8 +477,14 @@ int vr_evaluate_host(vr_ctx* ctx, const float* patches_host, const float* center
     rc = vr_bank_register(ctx, (const float*)d_p, (const float*)d_c, (const float*)d_r, (const int64_t*)d_l,
                           (const int32_t*)d_np, n, c, r);
     if (rc) return rc;
-    return vr_evaluate_registered(ctx, q_start, q_stride, nq, trunc_nums_host, n_trunc, max_np, p, tallies_host,
-                                  per_query_niter_host, st);
+    ctx->pending_wait = true;
+    rc = vr_evaluate_registered(ctx, q_start, q_stride, nq, trunc_nums_host, n_trunc, max_np, p, tallies_host,
+                                per_query_niter_host, st);
+    if (ctx->pending_wait) {   // no rerank ran (K = 0): still do not return before the upload has finished
+        ctx->pending_wait = false;
+        VR_CHECK_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    }
+    return rc;
 }
 
 }  // extern "C"
