@@ -100,6 +100,12 @@ PAIR_CASES = [
     ("soft", dict(use_cls_token=True), 12, 0.6),
     ("relu", dict(use_cls_token=False), 12, 0.6),
     ("rollout", dict(), 104, 0.3),
+    # shortlist lengths around the CTA / warp boundaries of the 7 x 16 pair slots
+    ("rollout", dict(), 1, 0.6),
+    ("rollout", dict(), 17, 0.6),
+    ("rollout", dict(), 97, 0.6),
+    ("rollout", dict(), 112, 0.6),
+    ("uniform", dict(), 33, 1.0),
 ]
 
 

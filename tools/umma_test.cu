@@ -196,6 +196,23 @@ __global__ void __launch_bounds__(128, 1) umma16_kernel(const float* A, const fl
     const uint32_t tm = tbase;
     // D = F32 (bit 4), A = B = F16 (format 0), K-major, N >> 3 at bit 17, M >> 4 at bit 24
     const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    if (tid == 0 && nterms == 3) {   // execution time of 24 MMAs versus the A-operand strides (values are garbage here)
+        const uint32_t lbos[5] = {2048, 128, 128, 128, 128}, sbos[5] = {128, 256, 512, 1024, 2048};
+        for (int v = 0; v < 5; v++) {
+            const uint64_t ad = make_desc(smem_u32(Ahi), lbos[v], sbos[v]);
+            const uint64_t bd = make_desc(smem_u32(Bhi), 64 * 16, 128);
+            const long long t0 = clock64();
+            for (int i = 0; i < 24; i++)
+                asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                             ::"r"(tm), "l"(ad + (uint64_t)(i & 3) * 16), "l"(bd), "r"(idesc), "r"(1u) : "memory");
+            const long long t1 = clock64();
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+            asm volatile("{\n.reg .pred p;\nW5:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DN5;\nbra W5;\nDN5:\n}\n" ::"r"(smem_u32(&bar)), "r"(v & 1) : "memory");
+            const long long t2 = clock64();
+            printf("  24 f16 MMAs (128x64x16), A LBO %4u SBO %4u: issue %lld, until complete %lld cycles\n", lbos[v], sbos[v], t1 - t0, t2 - t0);
+        }
+    }
+    const uint32_t wait_parity = (nterms == 3) ? 1u : 0u;
     if (tid == 0) {
         for (int ks = 0; ks < NK16; ks++) {
             const uint64_t ah = make_desc(smem_u32(Ahi + ks * 128 * 16), 128 * 16, 128);
@@ -214,7 +231,7 @@ __global__ void __launch_bounds__(128, 1) umma16_kernel(const float* A, const fl
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
     }
-    asm volatile("{\n.reg .pred p;\nW3:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DN3;\nbra W3;\nDN3:\n}\n" ::"r"(smem_u32(&bar)), "r"(0) : "memory");
+    asm volatile("{\n.reg .pred p;\nW3:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DN3;\nbra W3;\nDN3:\n}\n" ::"r"(smem_u32(&bar)), "r"(wait_parity) : "memory");
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t taddr = tm + ((uint32_t)(32 * warp) << 16);
     for (int c0 = 0; c0 < N; c0 += 16) {
