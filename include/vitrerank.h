@@ -84,7 +84,10 @@ VR_API int vr_device_info(vr_ctx* ctx, int32_t* sm_count, int32_t* max_active_cl
  * Replaces the bank construction at eval_cvt_diml.py:299-308 (banks are already
  * L2-normalised by the caller as at :304-305).  rollout / labels / num_pos may be NULL
  * when the mode / entry points used do not need them.  num_pos[i] = #{j : labels[j] ==
- * labels[i]} (metrics.py:34), int32. */
+ * labels[i]} (metrics.py:34), int32.
+ * Only pointers are recorded here.  The first fused rerank afterwards derives a library-owned
+ * fp16 copy of `patches` in the operand layout of the patch-similarity kernel (64 KB per image,
+ * on that call's stream); register again after modifying a registered bank in place. */
 VR_API int vr_bank_register(vr_ctx* ctx, const float* patches, const float* centers, const float* rollout,
                      const int64_t* labels, const int32_t* num_pos, int64_t n, int32_t c, int32_t r);
 
