@@ -17,6 +17,7 @@ constexpr int S0_BN = 64;      // gallery columns per tile
 constexpr int S0_BK = 32;      // channels per pipeline stage
 constexpr int S0_LD = 36;      // padded smem row stride (floats): conflict-free LDS.128
 constexpr int S0_THREADS = 256;
+constexpr int S0_STAGES = 3;   // cp.async ring: one CTA barrier per chunk instead of two
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes)
@@ -45,9 +46,9 @@ __global__ void __launch_bounds__(S0_THREADS, 2) stage0_select_kernel(Stage0Args
     constexpr int CN = S0_BN / TX;
     static_assert(TY * TX == S0_THREADS, "thread grid");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* As = reinterpret_cast<float*>(smem_raw);                 // [2][BM][LD]
-    float* Bs = As + 2 * BM * S0_LD;                                // [2][BN][LD]
-    unsigned long long* buf = reinterpret_cast<unsigned long long*>(Bs + 2 * S0_BN * S0_LD);  // [BM][P]
+    float* As = reinterpret_cast<float*>(smem_raw);                 // [3][BM][LD]
+    float* Bs = As + S0_STAGES * BM * S0_LD;                        // [3][BN][LD]
+    unsigned long long* buf = reinterpret_cast<unsigned long long*>(Bs + S0_STAGES * S0_BN * S0_LD);  // [BM][P]
     unsigned long long* thr = buf + (size_t)BM * a.P;               // [BM]
     int* cnt = reinterpret_cast<int*>(thr + BM);                    // [BM]
     long long* selfs = reinterpret_cast<long long*>(cnt + BM + (BM & 1));  // [BM]
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(S0_THREADS, 2) stage0_select_kernel(Stage0Args
     }
 
     auto issue = [&](int it) {
-        const int tile = it / KC, kc = it % KC, st = it & 1;
+        const int tile = it / KC, kc = it % KC, st = it % S0_STAGES;
         const int64_t n0 = (tile_lo + tile) * S0_BN;
         const int k0 = kc * S0_BK;
         float* as = As + st * BM * S0_LD;
@@ -117,17 +118,16 @@ __global__ void __launch_bounds__(S0_THREADS, 2) stage0_select_kernel(Stage0Args
 
     const int total = ntiles * KC;
     if (total > 0) issue(0);
-    __syncthreads();  // cnt/thr/selfs visible
+    if (total > 1) issue(1);
     for (int it = 0; it < total; it++) {
-        if (it + 1 < total) {
-            issue(it + 1);
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
+        if (it + 1 < total) cp_async_wait<1>();
+        else cp_async_wait<0>();
+        // one barrier per chunk: chunk `it` has landed for everybody, and everybody is done with chunk it-1, whose
+        // stage is the one chunk it+2 goes to (it also publishes cnt / thr / selfs and the sorts of the last tile)
         __syncthreads();
-        const float* as = As + (it & 1) * BM * S0_LD;
-        const float* bs = Bs + (it & 1) * S0_BN * S0_LD;
+        if (it + 2 < total) issue(it + 2);
+        const float* as = As + (it % S0_STAGES) * BM * S0_LD;
+        const float* bs = Bs + (it % S0_STAGES) * S0_BN * S0_LD;
 #pragma unroll
         for (int k4 = 0; k4 < S0_BK / 4; k4++) {
             float4 av[RM], bv[CN];
@@ -183,8 +183,8 @@ __global__ void __launch_bounds__(S0_THREADS, 2) stage0_select_kernel(Stage0Args
                 }
             }
         }
-        __syncthreads();
     }
+    __syncthreads();
 
     // ---- final per-row sort and write-out ----
     for (int r = warp; r < BM; r += S0_THREADS / 32) {
@@ -259,7 +259,7 @@ static Stage0Plan plan_stage0(int64_t nq, int64_t n, int kp, int sms) {
     const size_t budget = 110 * 1024;
     pl.bm = 64;
     for (;;) {
-        size_t ops = (size_t)2 * (pl.bm + S0_BN) * S0_LD * 4;
+        size_t ops = (size_t)S0_STAGES * (pl.bm + S0_BN) * S0_LD * 4;
         size_t keys = (size_t)pl.bm * pl.P * 8 + (size_t)pl.bm * (8 + 4 + 8) + 16;
         pl.smem = ops + keys;
         if (pl.smem <= budget || pl.bm == 8) break;
