@@ -68,7 +68,7 @@ int main(int argc, char** argv) {
     a.q_patches = d_bank; a.c_patches = d_bank; a.q_rollout = d_roll; a.c_rollout = d_roll;
     a.cand_idx = d_cand; a.cand_stride = k; a.q_start = 0; a.q_stride = 1; a.k = k;
     a.p.mode = VR_MODE_ROLLOUT; a.p.use_cls_token = 1; a.p.ot_temp = 0.05f; a.p.temperature = 0.1f; a.p.ot_part = 1.0f;
-    a.p.max_iter = argc > 5 ? atoi(argv[5]) : 100; a.p.thresh = 0.1f;
+    a.p.max_iter = argc > 5 ? atoi(argv[5]) : 100; a.p.thresh = argc > 7 ? atof(argv[7]) : 0.1f;
     a.out_score = d_score; a.out_niter = d_niter;
 #ifdef PR_TIMING
     a.dbg_clk = d_clk;
@@ -125,6 +125,9 @@ int main(int argc, char** argv) {
     double wc = 0, wn = 0;
     for (int q = 0; q < nq; q++) { wc += (double)clk[q * 16 + 9]; wn += (double)clk[q * 16 + 15]; }
     printf("  exchange re-polls of thread 0 per query: %.1f in steps 0..3, %.1f later\n", wc / nq, wn / nq);
+    double fs = 0;
+    for (int q = 0; q < nq; q++) fs += (double)clk[q * 16 + 8];
+    printf("  fetch check (first look at the fetched partials, thread 0): %.0f cycles per iteration\n", fs / nq / (mi + 2));
     printf("  loop per iteration: %.0f cycles; whole CTA after setup: %.0f cycles\n", ph[4] / nq / mi, tot / nq);
 #endif
     return 0;
