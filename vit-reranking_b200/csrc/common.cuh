@@ -85,7 +85,7 @@ __device__ __forceinline__ void warp_bitonic_sort_desc(unsigned long long* a, in
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             __syncwarp();
             for (int t = lane; t < (n >> 1); t += 32) {
-                int lo = ((t / stride) * (stride << 1)) + (t % stride);
+                int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));   // stride is a power of two
                 int hi = lo + stride;
                 bool desc = ((lo & size) == 0);
                 unsigned long long x = a[lo], y = a[hi];

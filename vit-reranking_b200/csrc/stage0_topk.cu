@@ -8,6 +8,7 @@
 //
 // Arithmetic: plain fp32 FMA, sequential over the C channels (no TF32: the top-K sets
 // must match the reference's fp32 path, SURVEY.md section 7 hard part 3).
+#include <algorithm>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -207,6 +208,164 @@ __global__ void __launch_bounds__(S0_THREADS, 2) stage0_select_kernel(Stage0Args
     }
 }
 
+// ---- large query batches: score chunk by a register-tiled SGEMM, then one warp per row selects ----
+// The fused kernel above keeps BM x P keys of candidate buffers in shared memory, which caps its row block at 32 and its
+// register tile at 2 x 4: 6 LDS.128 per 32 FMAs, shared-memory bound, and the buffer sorts of single warps stall whole
+// CTAs at the chunk barrier.  For batches that fill the GPU the work is split instead: this kernel is a plain 128 x 64
+// SGEMM tile (8 x 4 per thread: 12 LDS.128 per 128 FMAs) that writes a [rows, ld] score chunk sized to stay in L2, and
+// stage0_rowselect_kernel streams each row once.  Every score is the same sequential fp32 FMA chain over the channels, so
+// both paths return identical shortlists.
+constexpr int S0G_BM = 128;
+template <int TY, int TX>
+__global__ void __launch_bounds__(S0_THREADS, 2) stage0_scores_kernel(Stage0Args a, int64_t r_begin, int64_t rows, int tiles_per,
+                                                                      float* __restrict__ scores, int64_t ld) {
+    constexpr int BM = S0G_BM;
+    constexpr int RM = BM / TY;
+    constexpr int CN = S0_BN / TX;
+    static_assert(TY * TX == S0_THREADS, "thread grid");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* As = reinterpret_cast<float*>(smem_raw);                 // [3][BM][LD]
+    float* Bs = As + S0_STAGES * BM * S0_LD;                        // [3][BN][LD]
+    const int tid = threadIdx.x;
+    const int tx = tid % TX, ty = tid / TX;
+    const int64_t row0 = (int64_t)blockIdx.y * BM;                  // row of the chunk
+    const int C = a.c;
+    const int64_t tiles_total = (a.n + S0_BN - 1) / S0_BN;
+    const int64_t tile_lo = (int64_t)blockIdx.x * tiles_per;
+    const int ntiles = (int)max((int64_t)0, min(tiles_total, tile_lo + tiles_per) - tile_lo);
+    const int KC = (C + S0_BK - 1) / S0_BK;
+
+    auto issue = [&](int it) {
+        const int tile = it / KC, kc = it % KC, st = it % S0_STAGES;
+        const int64_t n0 = (tile_lo + tile) * S0_BN;
+        const int k0 = kc * S0_BK;
+        float* as = As + st * BM * S0_LD;
+        float* bs = Bs + st * S0_BN * S0_LD;
+        for (int e = tid; e < BM * (S0_BK / 4); e += S0_THREADS) {
+            int r = e / (S0_BK / 4), q4 = e % (S0_BK / 4);
+            int64_t g = r_begin + row0 + r;
+            int k = k0 + q4 * 4;
+            const float* src = a.centers;
+            int bytes = 0;
+            if (row0 + r < rows && k < C) {
+                src = a.q_centers ? a.q_centers + g * C + k : a.centers + (a.q_start + g * a.q_stride) * C + k;
+                bytes = 16;
+            }
+            cp_async16(as + r * S0_LD + q4 * 4, src, bytes);
+        }
+        for (int e = tid; e < S0_BN * (S0_BK / 4); e += S0_THREADS) {
+            int r = e / (S0_BK / 4), q4 = e % (S0_BK / 4);
+            int64_t g = n0 + r;
+            int k = k0 + q4 * 4;
+            const float* src = a.centers;
+            int bytes = 0;
+            if (g < a.n && k < C) {
+                src = a.centers + g * C + k;
+                bytes = 16;
+            }
+            cp_async16(bs + r * S0_LD + q4 * 4, src, bytes);
+        }
+        cp_async_commit();
+    };
+
+    float acc[RM][CN];
+#pragma unroll
+    for (int i = 0; i < RM; i++)
+#pragma unroll
+        for (int j = 0; j < CN; j++) acc[i][j] = 0.f;
+
+    const int total = ntiles * KC;
+    if (total > 0) issue(0);
+    if (total > 1) issue(1);
+    for (int it = 0; it < total; it++) {
+        if (it + 1 < total) cp_async_wait<1>();
+        else cp_async_wait<0>();
+        __syncthreads();   // chunk `it` has landed for everybody, and everybody is done with the stage chunk it+2 goes to
+        if (it + 2 < total) issue(it + 2);
+        const float* as = As + (it % S0_STAGES) * BM * S0_LD;
+        const float* bs = Bs + (it % S0_STAGES) * S0_BN * S0_LD;
+#pragma unroll
+        for (int k4 = 0; k4 < S0_BK / 4; k4++) {
+            float4 av[RM], bv[CN];
+#pragma unroll
+            for (int i = 0; i < RM; i++) av[i] = *reinterpret_cast<const float4*>(as + (ty + TY * i) * S0_LD + k4 * 4);
+#pragma unroll
+            for (int j = 0; j < CN; j++) bv[j] = *reinterpret_cast<const float4*>(bs + (tx + TX * j) * S0_LD + k4 * 4);
+#pragma unroll
+            for (int i = 0; i < RM; i++)
+#pragma unroll
+                for (int j = 0; j < CN; j++) {
+                    acc[i][j] = fmaf(av[i].x, bv[j].x, acc[i][j]);
+                    acc[i][j] = fmaf(av[i].y, bv[j].y, acc[i][j]);
+                    acc[i][j] = fmaf(av[i].z, bv[j].z, acc[i][j]);
+                    acc[i][j] = fmaf(av[i].w, bv[j].w, acc[i][j]);
+                }
+        }
+        if (it % KC == KC - 1) {
+            const int64_t n0 = (tile_lo + it / KC) * S0_BN;
+#pragma unroll
+            for (int i = 0; i < RM; i++) {
+                const int64_t r = row0 + ty + TY * i;
+#pragma unroll
+                for (int j = 0; j < CN; j++) {
+                    const int64_t col = n0 + tx + TX * j;
+                    if (r < rows && col < a.n) scores[r * ld + col] = acc[i][j];
+                    acc[i][j] = 0.f;
+                }
+            }
+        }
+    }
+}
+
+// One warp per row of the score chunk: self mask (eval_cvt_diml.py:327), streaming top-kp select with a running
+// threshold (survivors go to a P-key buffer that is re-sorted when 64 more might not fit), final sort, write-out.
+__global__ void stage0_rowselect_kernel(Stage0Args a, int64_t r_begin, int64_t rows, const float* __restrict__ scores, int64_t ld) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int P = a.P, kp = a.kp;
+    unsigned long long* b = reinterpret_cast<unsigned long long*>(smem_raw) + (size_t)warp * P;
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (r >= rows) return;
+    const int64_t g = r_begin + r;
+    long long self = -1;
+    if (a.self_idx) self = a.self_idx[g];
+    else if (!a.q_centers) self = a.q_start + g * a.q_stride;
+    const float* srow = scores + r * ld;
+    unsigned long long thr = 0ull;
+    int cnt = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int64_t base = 0; base < a.n; base += 64) {
+        if (cnt > P - 64) {
+            for (int e = cnt + lane; e < P; e += 32) b[e] = 0ull;
+            warp_bitonic_sort_desc(b, P, lane);
+            cnt = min(cnt, kp);
+            if (cnt >= kp) thr = b[kp - 1];
+            __syncwarp();
+        }
+        const int64_t col0 = base + 2 * lane;
+        float2 v = make_float2(0.f, 0.f);
+        if (col0 < ld) v = *reinterpret_cast<const float2*>(srow + col0);   // ld is even: col0 + 1 < ld too
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+            const int64_t col = col0 + t;
+            float s = t ? v.y : v.x;
+            if (col == self) s = -100.0f;
+            const unsigned long long key = pack_key(s, (uint32_t)col);
+            const bool take = col < a.n && key > thr;
+            const unsigned m = __ballot_sync(0xffffffffu, take);
+            if (take) b[cnt + __popc(m & lt)] = key;
+            cnt += __popc(m);
+        }
+    }
+    for (int e = cnt + lane; e < P; e += 32) b[e] = 0ull;
+    warp_bitonic_sort_desc(b, P, lane);
+    for (int e = lane; e < kp; e += 32) {
+        const unsigned long long key = b[e];
+        a.out_idx[g * kp + e] = key ? (int32_t)key_index(key) : -1;
+        a.out_score[g * kp + e] = key ? key_score(key) : 0.f;
+    }
+}
+
 // Merge the nsplit partial shortlists of every query (one warp per query).
 __global__ void stage0_merge_kernel(const unsigned long long* partial, int64_t nq, int nsplit, int kp, int P2,
                                     int32_t* out_idx, float* out_score) {
@@ -277,8 +436,34 @@ static Stage0Plan plan_stage0(int64_t nq, int64_t n, int kp, int sms) {
     return pl;
 }
 
+// Two-kernel path: used for batches of at least 256 queries.  The score chunk is sized to stay resident in L2.
+struct Stage0GemmPlan {
+    bool use;
+    int64_t rows, ld;   // rows per chunk (multiple of 128), row stride of the score chunk (floats, multiple of 4)
+    int P, warps;
+    size_t smem_sel, ws_bytes;
+};
+static Stage0GemmPlan plan_stage0_gemm(int64_t nq, int64_t n, int kp) {
+    Stage0GemmPlan g{};
+    g.use = nq >= 256;
+    if (!g.use) return g;
+    g.ld = (n + 3) & ~(int64_t)3;
+    const int64_t target = 64ll << 20;   // bytes of scores per chunk: about half of the 126 MB L2
+    int64_t rows = target / (g.ld * 4) / S0G_BM * S0G_BM;
+    rows = std::max<int64_t>(rows, S0G_BM);
+    rows = std::min<int64_t>(rows, (nq + S0G_BM - 1) / S0G_BM * S0G_BM);
+    g.rows = rows;
+    g.P = next_pow2(kp + 64);
+    g.warps = 8;
+    while (g.warps > 1 && (size_t)g.warps * g.P * 8 > 96 * 1024) g.warps >>= 1;
+    g.smem_sel = (size_t)g.warps * g.P * 8;
+    g.ws_bytes = (size_t)rows * g.ld * 4;
+    return g;
+}
+
 size_t stage0_workspace_bytes(int64_t nq, int64_t n, int kp, int sms) {
-    return align_up(plan_stage0(nq, n, kp, sms).ws_bytes, 256) + 256;
+    const size_t fused = plan_stage0(nq, n, kp, sms).ws_bytes, gemm = plan_stage0_gemm(nq, n, kp).ws_bytes;
+    return align_up(std::max(fused, gemm), 256) + 256;
 }
 
 template <int BM, int TY, int TX>
@@ -318,6 +503,33 @@ int stage0_topk(const float* q_centers, const int64_t* self_idx, const float* ce
     a.n = n;
     a.c = c;
     a.kp = kp;
+    const Stage0GemmPlan gp = plan_stage0_gemm(nq, n, kp);
+    if (gp.use && gp.ws_bytes <= ws_bytes) {
+        a.P = gp.P;
+        a.nsplit = 1;
+        a.partial = nullptr;
+        a.out_idx = out_idx;
+        a.out_score = out_score;
+        float* scores = reinterpret_cast<float*>(ws);
+        const size_t smem_g = (size_t)S0_STAGES * (S0G_BM + S0_BN) * S0_LD * 4;
+        VR_CHECK_CUDA(cudaFuncSetAttribute(stage0_scores_kernel<16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+        VR_CHECK_CUDA(cudaFuncSetAttribute(stage0_rowselect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gp.smem_sel));
+        const int64_t tiles_total = (n + S0_BN - 1) / S0_BN;
+        for (int64_t r0 = 0; r0 < nq; r0 += gp.rows) {
+            const int64_t rows = std::min(gp.rows, nq - r0);
+            const int64_t row_blocks = (rows + S0G_BM - 1) / S0G_BM;
+            // column groups: about four CTAs per SM in the grid, at least two column tiles per CTA
+            int64_t groups = std::min<int64_t>(tiles_total, std::max<int64_t>(1, (4ll * sms + row_blocks - 1) / row_blocks));
+            int tiles_per = (int)std::max<int64_t>(2, (tiles_total + groups - 1) / groups);
+            groups = (tiles_total + tiles_per - 1) / tiles_per;
+            dim3 grid((unsigned)groups, (unsigned)row_blocks);
+            stage0_scores_kernel<16, 16><<<grid, S0_THREADS, smem_g, st>>>(a, r0, rows, tiles_per, scores, gp.ld);
+            VR_LAUNCH_CHECK();
+            stage0_rowselect_kernel<<<(unsigned)((rows + gp.warps - 1) / gp.warps), gp.warps * 32, gp.smem_sel, st>>>(a, r0, rows, scores, gp.ld);
+            VR_LAUNCH_CHECK();
+        }
+        return VR_OK;
+    }
     a.P = pl.P;
     a.nsplit = pl.nsplit;
     a.partial = reinterpret_cast<unsigned long long*>(ws);
