@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(S0_THREADS, 2) stage0_select_kernel(Stage0Args
 // The fused kernel above keeps BM x P keys of candidate buffers in shared memory, which caps its row block at 32 and its
 // register tile at 2 x 4: 6 LDS.128 per 32 FMAs, shared-memory bound, and the buffer sorts of single warps stall whole
 // CTAs at the chunk barrier.  For batches that fill the GPU the work is split instead: this kernel is a plain 128 x 64
-// SGEMM tile (8 x 4 per thread: 12 LDS.128 per 128 FMAs) that writes a [rows, ld] score chunk sized to stay in L2, and
+// SGEMM tile (8 x 4 per thread: 12 LDS.128 per 128 FMAs) that writes a [rows, ld] score chunk to the workspace, and
 // stage0_rowselect_kernel streams each row once.  Every score is the same sequential fp32 FMA chain over the channels, so
 // both paths return identical shortlists.
 constexpr int S0G_BM = 128;
@@ -334,28 +334,45 @@ __global__ void stage0_rowselect_kernel(Stage0Args a, int64_t r_begin, int64_t r
     unsigned long long thr = 0ull;
     int cnt = 0;
     const unsigned lt = (1u << lane) - 1u;
-    for (int64_t base = 0; base < a.n; base += 64) {
-        if (cnt > P - 64) {
-            for (int e = cnt + lane; e < P; e += 32) b[e] = 0ull;
-            warp_bitonic_sort_desc(b, P, lane);
-            cnt = min(cnt, kp);
-            if (cnt >= kp) thr = b[kp - 1];
-            __syncwarp();
-        }
-        const int64_t col0 = base + 2 * lane;
-        float2 v = make_float2(0.f, 0.f);
-        if (col0 < ld) v = *reinterpret_cast<const float2*>(srow + col0);   // ld is even: col0 + 1 < ld too
+    // 256 scores per step, as four groups of 64 (the buffer check is per group); the next step's loads are in flight
+    // while this one is filtered, so the L2 / HBM latency is paid once per row, not once per group
+    auto load4 = [&](float2 (&d)[4], int64_t base) {
 #pragma unroll
-        for (int t = 0; t < 2; t++) {
-            const int64_t col = col0 + t;
-            float s = t ? v.y : v.x;
-            if (col == self) s = -100.0f;
-            const unsigned long long key = pack_key(s, (uint32_t)col);
-            const bool take = col < a.n && key > thr;
-            const unsigned m = __ballot_sync(0xffffffffu, take);
-            if (take) b[cnt + __popc(m & lt)] = key;
-            cnt += __popc(m);
+        for (int u = 0; u < 4; u++) {
+            const int64_t col0 = base + 64 * u + 2 * lane;
+            d[u] = make_float2(0.f, 0.f);
+            if (col0 < ld) d[u] = __ldcs(reinterpret_cast<const float2*>(srow + col0));   // ld is even: col0 + 1 < ld too
         }
+    };
+    float2 cur[4], nxt[4];
+    load4(cur, 0);
+    for (int64_t base = 0; base < a.n; base += 256) {
+        if (base + 256 < a.n) load4(nxt, base + 256);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (base + 64 * u >= a.n) break;
+            if (cnt > P - 64) {
+                for (int e = cnt + lane; e < P; e += 32) b[e] = 0ull;
+                warp_bitonic_sort_desc(b, P, lane);
+                cnt = min(cnt, kp);
+                if (cnt >= kp) thr = b[kp - 1];
+                __syncwarp();
+            }
+            const int64_t col0 = base + 64 * u + 2 * lane;
+#pragma unroll
+            for (int t = 0; t < 2; t++) {
+                const int64_t col = col0 + t;
+                float s = t ? cur[u].y : cur[u].x;
+                if (col == self) s = -100.0f;
+                const unsigned long long key = pack_key(s, (uint32_t)col);
+                const bool take = col < a.n && key > thr;
+                const unsigned m = __ballot_sync(0xffffffffu, take);
+                if (take) b[cnt + __popc(m & lt)] = key;
+                cnt += __popc(m);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) cur[u] = nxt[u];
     }
     for (int e = cnt + lane; e < P; e += 32) b[e] = 0ull;
     warp_bitonic_sort_desc(b, P, lane);
@@ -436,7 +453,7 @@ static Stage0Plan plan_stage0(int64_t nq, int64_t n, int kp, int sms) {
     return pl;
 }
 
-// Two-kernel path: used for batches of at least 256 queries.  The score chunk is sized to stay resident in L2.
+// Two-kernel path: used for batches of at least 256 queries.
 struct Stage0GemmPlan {
     bool use;
     int64_t rows, ld;   // rows per chunk (multiple of 128), row stride of the score chunk (floats, multiple of 4)
@@ -448,9 +465,12 @@ static Stage0GemmPlan plan_stage0_gemm(int64_t nq, int64_t n, int kp) {
     g.use = nq >= 256;
     if (!g.use) return g;
     g.ld = (n + 3) & ~(int64_t)3;
-    const int64_t target = 64ll << 20;   // bytes of scores per chunk: about half of the 126 MB L2
+    // bytes of scores per chunk: large enough that the row select has a warp for every scheduler slot of the GPU
+    // (8,192 rows); the HBM round trip of the chunk costs ~3 % of the SGEMM's time
+    const int64_t target = 1ll << 30;
     int64_t rows = target / (g.ld * 4) / S0G_BM * S0G_BM;
     rows = std::max<int64_t>(rows, S0G_BM);
+    rows = std::min<int64_t>(rows, 8192);
     rows = std::min<int64_t>(rows, (nq + S0G_BM - 1) / S0G_BM * S0G_BM);
     g.rows = rows;
     g.P = next_pow2(kp + 64);
@@ -518,8 +538,8 @@ int stage0_topk(const float* q_centers, const int64_t* self_idx, const float* ce
         for (int64_t r0 = 0; r0 < nq; r0 += gp.rows) {
             const int64_t rows = std::min(gp.rows, nq - r0);
             const int64_t row_blocks = (rows + S0G_BM - 1) / S0G_BM;
-            // column groups: about four CTAs per SM in the grid, at least two column tiles per CTA
-            int64_t groups = std::min<int64_t>(tiles_total, std::max<int64_t>(1, (4ll * sms + row_blocks - 1) / row_blocks));
+            // column groups: about sixteen CTAs per SM in the grid (a short tail), at least two column tiles per CTA
+            int64_t groups = std::min<int64_t>(tiles_total, std::max<int64_t>(1, (16ll * sms + row_blocks - 1) / row_blocks));
             int tiles_per = (int)std::max<int64_t>(2, (tiles_total + groups - 1) / groups);
             groups = (tiles_total + tiles_per - 1) / tiles_per;
             dim3 grid((unsigned)groups, (unsigned)row_blocks);
