@@ -265,30 +265,33 @@ def main():
     # ---- end to end through the host-buffer entry ----
     e2e = None
     if not args.no_e2e:
+        from vitrerank import distributed as vdist
         pin = gal.pin()
-        h2d = sum(t.numel() * t.element_size() for t in (pin.patches, pin.centers, pin.rollout, pin.labels)) + n * 4
         d2h = len(truncs) * 8 * 8
+
+        def e2e_step():
+            # world == 1: vr_evaluate_host (the C-ABI host-buffer entry).  world > 1: every image crosses PCIe once per
+            # node (this rank uploads its 1/W of the patch bank), NVLink all-gather, tallies all-reduced.
+            return vdist.evaluate_host_sharded(eng, pin.patches, pin.centers, pin.rollout, pin.labels, truncs, params)
+
         for _ in range(2):
-            eng.evaluate_host(pin.patches, pin.centers, pin.rollout, pin.labels, truncs, params, q_start=rank,
-                              q_stride=world, nq=nq)
+            tal_h, h2d = e2e_step()
         sync_all()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            tal_h = eng.evaluate_host(pin.patches, pin.centers, pin.rollout, pin.labels, truncs, params,
-                                      q_start=rank, q_stride=world, nq=nq)
-            if world > 1:
-                th = torch.from_numpy(tal_h).to(dev)
-                dist.all_reduce(th)
-                tal_h = th.cpu().numpy()
+            tal_h, h2d = e2e_step()
         sync_all()
         dt = time.perf_counter() - t0
         t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
         dt = float(t_e.item())
+        assert np.allclose(tal_h, tallies.numpy(), rtol=0, atol=1e-9), "end-to-end tallies differ from the resident pass"
         e2e = {"value": pairs_per_step * args.steps / dt, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * dt / args.steps,
-               "note": "vr_evaluate_host: pinned host banks -> HBM, S1..S5, tallies -> host; per rank"}
+               "note": ("vr_evaluate_host: pinned host banks -> HBM, S1..S5, tallies -> host" if world == 1 else
+                        "evaluate_host_sharded: each rank uploads 1/W of the patch bank (bytes are per rank), NVLink all-gather, "
+                        "S1..S5 on its query shard, tallies all-reduced -> host")}
         launches_e2e = _lib.take_launch_count()
         eng.register(gal.patches, gal.centers, gal.rollout, gal.labels)
     else:

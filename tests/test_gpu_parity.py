@@ -364,3 +364,63 @@ def test_exchange_transports_agree(eng, monkeypatch):
     torch.cuda.synchronize()
     assert torch.equal(n_g.cpu(), n_c.cpu())
     assert torch.equal(s_g.cpu(), s_c.cpu())
+
+
+def test_evaluate_host_sharded_single_rank(eng):
+    """Without a process group the sharded host entry is evaluate_host on the whole query set."""
+    from vitrerank import distributed as vd
+    from vitrerank.engine import OTParams
+    g = synth.make_gallery(260, 128, 49, classes=9, seed=5, sigma=0.6)
+    p = OTParams(mode="rollout")
+    eng.register(g.patches, g.centers, g.rollout, g.labels)
+    a = eng.evaluate([0, 100], p)
+    gp = g.pin()
+    b, h2d = vd.evaluate_host_sharded(eng, gp.patches, gp.centers, gp.rollout, gp.labels, [0, 100], p)
+    np.testing.assert_array_equal(a, b)
+    assert h2d == 260 * 128 * 49 * 4 + 260 * 128 * 4 + 260 * 49 * 4 + 260 * 8
+
+
+NCCL_WORKER = '''
+import os, sys, json
+sys.path.insert(0, {root!r}); sys.path.insert(0, {pkg!r})
+import numpy as np, torch, torch.distributed as dist
+from vitrerank import synth, distributed as vd
+from vitrerank.engine import OTParams, RerankEngine
+rank = int(sys.argv[1])
+torch.cuda.set_device(rank)
+dev = torch.device("cuda", rank)
+dist.init_process_group("nccl", init_method="tcp://127.0.0.1:{port}", rank=rank, world_size=2, device_id=dev)
+g = synth.make_gallery(301, 128, 49, classes=9, seed=5, sigma=0.6)    # odd size: the last rank uploads one image less
+eng = RerankEngine.get(dev)
+gp = g.pin()
+p = OTParams(mode="rollout")
+for _ in range(2):   # the second pass reuses the staging buffer
+    t, h2d = vd.evaluate_host_sharded(eng, gp.patches, gp.centers, gp.rollout, gp.labels, [0, 100], p)
+eng.register(g.patches, g.centers, g.rollout, g.labels)
+whole = eng.evaluate([0, 100], p)
+if rank == 0:
+    json.dump(dict(t=t.tolist(), whole=whole.tolist(), h2d=int(h2d)), open({out!r}, "w"))
+dist.barrier(); dist.destroy_process_group()
+'''
+
+
+def test_evaluate_host_sharded_two_rank_nccl(tmp_path):
+    """Each rank uploads half of the patch bank, NVLink all-gather, query shards, tally all-reduce:
+    same tallies as one GPU over the whole gallery.  Needs two GPUs (skipped on a one-GPU box)."""
+    import json
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "vit-reranking_b200")
+    out = str(tmp_path / "t.json")
+    script = tmp_path / "worker.py"
+    script.write_text(NCCL_WORKER.format(root=root, pkg=pkg, port=29600 + (os.getpid() % 2000), out=out))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)]) for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=300) == 0
+    got = json.load(open(out))
+    np.testing.assert_allclose(np.array(got["t"]), np.array(got["whole"]), rtol=1e-12)
+    assert got["h2d"] == 151 * 128 * 49 * 4 + 301 * 128 * 4 + 301 * 49 * 4 + 301 * 8
