@@ -83,6 +83,26 @@ def test_stage0_topk(eng, n, c, kp):
     assert near_tie_rows <= max(1, n // 200)
 
 
+def test_stage0_batch_and_small_paths_agree(eng):
+    """>= 256 queries go through the SGEMM + row-select kernels, fewer through the fused select kernel:
+    same fp32 FMA chains, same keys, so the shortlists must be bit-identical; the same holds for explicit
+    query centres with a self index (the query != gallery form of S1) and for an interleaved shard."""
+    n, kp = 777, 124
+    g = synth.make_gallery(n, 128, 4, classes=25, seed=3, sigma=0.6)
+    eng.register(g.patches, g.centers, None, g.labels)
+    idx, score = eng.stage0_topk(kp)                       # batch path
+    for lo in range(0, n, 200):                            # fused path, 200 (or 177) queries at a time
+        cnt = min(200, n - lo)
+        i2, s2 = eng.stage0_topk(kp, q_start=lo, nq=cnt)
+        assert torch.equal(i2, idx[lo:lo + cnt]) and torch.equal(s2, score[lo:lo + cnt])
+    i3, s3 = eng.stage0_topk(kp, q_centers=g.centers, self_idx=torch.arange(n))
+    assert torch.equal(i3, idx) and torch.equal(s3, score)
+    i4, s4 = eng.stage0_topk(kp, q_start=1, q_stride=2)    # 388 queries: batch path on a strided shard
+    assert torch.equal(i4, idx[1::2]) and torch.equal(s4, score[1::2])
+    i5, _ = eng.stage0_topk(kp, q_centers=g.centers[:300])  # no self index: nothing is masked
+    assert (i5[:, 0].cpu() == torch.arange(300)).all()
+
+
 def _oracle_pair(g, mode, **kw):
     return O.structural_similarity(g.patches[0], g.centers[0], g.patches[1:], g.centers[1:], mode,
                                    q_rollout=g.rollout[0], c_rollout=g.rollout[1:], trace=True, **kw)
