@@ -271,6 +271,44 @@ def test_evaluate_matches_oracle(eng, n, classes, seed, sigma, truncs, flags):
     np.testing.assert_allclose(tal[:, 3:7] / scale, np.array(ref["recall_at_1_2_4_8"]), rtol=1e-7, atol=1e-7)
 
 
+@pytest.mark.parametrize("n,k,flags,nq", [
+    (140, 113, dict(use_rollout=True, ot_part=1.0), 10),
+    (300, 128, dict(use_rollout=True, ot_part=1.0), 10),
+    (560, 500, dict(use_inverse=True, temperature=0.1, use_cls_token=True, ot_part=1.0), 6),
+    (1040, 1024, dict(use_rollout=True, ot_part=1.0), 3),
+])
+def test_wide_shortlists_fused(eng, n, k, flags, nq):
+    """113..1,024 candidates per query: ceil(K / 16) CTAs per query with the CTA-level exchange.  Per-pair scores,
+    iteration counts and metrics of a strided query subset against the oracle."""
+    from vitrerank.engine import OTParams
+    g = synth.make_gallery(n, 128, 49, classes=max(3, n // 90), seed=n + k, sigma=0.6)
+    stride = n // nq
+    ids = list(range(0, n, stride))[:nq]
+    p = OTParams.from_flags(**flags)
+    eng.register(g.patches, g.centers, g.rollout, g.labels)
+    idx, approx = eng.stage0_topk(k, q_start=0, q_stride=stride, nq=nq)
+    score, niter = eng.rerank_scores(idx, k, p, q_start=0, q_stride=stride)
+    tal, _ = eng.finalize(idx, approx, score, k, [0, k], q_start=0, q_stride=stride)
+    idx, score, niter = idx.cpu().numpy(), score.cpu().numpy(), niter.cpu().numpy()
+    ref0 = O.evaluate_banks(g.patches, g.centers, g.rollout, g.labels, trunc_nums=[0, k], query_ids=ids, dump=True, **flags)
+    for q, d in enumerate(ref0["dump"]):
+        assert stop_ok(int(niter[q]), d["n_iter"], d["errs"]), (q, int(niter[q]), d["n_iter"], d["errs"][-3:])
+    ref = O.evaluate_banks(g.patches, g.centers, g.rollout, g.labels, trunc_nums=[0, k], query_ids=ids, dump=True,
+                           force_iters=niter, **flags)
+    worst = 0.0
+    for q, d in enumerate(ref["dump"]):
+        assert set(idx[q].tolist()) == set(d["top"].tolist())
+        pos = {int(c): i for i, c in enumerate(idx[q])}
+        mine = np.array([score[q, pos[int(c)]] for c in d["top"]])
+        worst = max(worst, rel_err(mine, d["score"].numpy()).max())
+    assert worst < SCORE_RTOL, worst
+    scale = n / 100.0
+    tal = tal.cpu().numpy()
+    assert tal[0, 7] == nq
+    for col, key in enumerate(("r1", "rp", "mapr")):
+        np.testing.assert_allclose(tal[:, col] / scale, ref[key], rtol=1e-6, atol=1e-7)
+
+
 def test_evaluate_stages_and_scores(eng):
     """Stage by stage on one gallery: shortlist sets, per-pair scores, reranked order."""
     from vitrerank.engine import OTParams

@@ -186,7 +186,7 @@ int vr_stage0_topk(vr_ctx* ctx, const float* q_centers, const int64_t* self_idx,
 
 size_t vr_rerank_workspace_bytes(vr_ctx* ctx, int64_t nq, int32_t k, const vr_ot_params* p) {
     if (!ctx || !p || ctx->n <= 0) return 0;
-    if (pair_fused_supports(ctx->c, ctx->r, k, p)) return 256;
+    if (pair_fused_supports(ctx->c, ctx->r, k, p) || (!ctx->dbg_err && pair_fused_supports_wide(ctx->c, ctx->r, k, p))) return 256;
     return generic_rerank_workspace_bytes(nq, k, ctx->r, p);
 }
 
@@ -210,7 +210,8 @@ int vr_rerank_scores(vr_ctx* ctx, int64_t q_start, int64_t q_stride, int64_t nq,
         VR_CHECK_CUDA(cudaStreamWaitEvent(st, ctx->patches_ready, 0));
         ctx->pending_wait = false;
     }
-    if (pair_fused_supports(ctx->c, ctx->r, k, p)) {
+    // (the err trace of vr_debug_err_trace is a diagnostics output: shortlists beyond 112 then take the generic solver)
+    if (pair_fused_supports(ctx->c, ctx->r, k, p) || (!ctx->dbg_err && pair_fused_supports_wide(ctx->c, ctx->r, k, p))) {
         PairArgs a{};
         a.q_patches = ctx->patches;
         a.q_centers = ctx->centers;
@@ -397,7 +398,8 @@ int vr_evaluate_registered(vr_ctx* ctx, int64_t q_start, int64_t q_stride, int64
 
     // chunk the queries so that per-chunk buffers stay bounded
     int64_t chunk = std::min<int64_t>(nq, 16384);
-    const bool fused = k > 0 && pair_fused_supports(ctx->c, ctx->r, k, p);
+    const bool fused = k > 0 && (pair_fused_supports(ctx->c, ctx->r, k, p) ||
+                                 (!ctx->dbg_err && pair_fused_supports_wide(ctx->c, ctx->r, k, p)));
     if (k > 0 && !fused) {
         size_t per_q = generic_rerank_workspace_bytes(1, k, ctx->r, p);
         chunk = std::max<int64_t>(1, std::min<int64_t>(chunk, (int64_t)((size_t)1536 * 1024 * 1024 / per_q)));

@@ -22,6 +22,7 @@ struct PairArgs {
     float* dbg_err;           // optional [nq, max_iter]: the stop-test value of every iteration
     long long* dbg_clk;       // optional [nq, 16]: phase clocks (only read by builds with -DPR_TIMING)
     unsigned long long* ex_part;   // exchange buffer of the global transport (set by pair_fused_launch)
+    int group_ctas;           // CTAs per query of the wide path, ceil(k / 16) (set by pair_fused_launch)
     const void* c_packed_a;   // re-packed candidate bank (pair_fused_repack) or nullptr: convert on the fly
     const void* q_packed_b;   // re-packed query bank, indexed by the query id
 };
@@ -65,6 +66,7 @@ int global_similarity(const float* q, const float* centers, int64_t n, int c, fl
 // pair_fused.cu
 int pair_fused_max_clusters(int* out);
 bool pair_fused_supports(int c, int r, int k, const vr_ot_params* p);
+bool pair_fused_supports_wide(int c, int r, int k, const vr_ot_params* p);   // 112 < k <= 1024, scores only
 int pair_fused_launch(const PairArgs& a, int64_t nq, cudaStream_t st);
 size_t pair_fused_packed_bytes(int64_t n);   // both roles
 int pair_fused_repack(const float* patches, int64_t n, void* packed, cudaStream_t st);
