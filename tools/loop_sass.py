@@ -1,10 +1,10 @@
 #!/usr/bin/env python
-"""Instruction mix of the Sinkhorn loop of pair_fused_kernel<false,true> in a built binary (cuobjdump -sass).
+"""Instruction mix of the Sinkhorn loop of pair_fused_kernel<false, 1> in a built binary (cuobjdump -sass).
 usage: loop_sass.py <binary> [--dump]"""
 import re, subprocess, sys, collections
 out = subprocess.run(["cuobjdump", "-sass", sys.argv[1]], capture_output=True, text=True).stdout
 funcs = re.split(r"\n\s*Function : ", out)
-body = next(f for f in funcs if f.startswith("_ZN2vr17pair_fused_kernelILb0ELb1"))
+body = next(f for f in funcs if f.startswith("_ZN2vr17pair_fused_kernelILb0ELi1"))
 ins = []
 for m in re.finditer(r"/\*([0-9a-f]{4,})\*/\s+(.*?);", body):
     ins.append((int(m.group(1), 16), m.group(2).strip()))
