@@ -482,3 +482,53 @@ def test_evaluate_host_sharded_two_rank_nccl(tmp_path):
     got = json.load(open(out))
     np.testing.assert_allclose(np.array(got["t"]), np.array(got["whole"]), rtol=1e-12)
     assert got["h2d"] == 151 * 128 * 49 * 4 + 301 * 128 * 4 + 301 * 49 * 4 + 301 * 8
+
+
+def test_full_size_properties_cars196(eng):
+    """BASELINE configs[1] at full size (8,131 images, K = 100, rollout marginals): the oracle needs minutes for the
+    whole pass, so the full-size run is checked through properties that do not depend on the size — sorted, duplicate-free,
+    self-free shortlists; bit-identical repeat (every sum in the path has a fixed order or is an integer sum); query shards
+    whose tallies add up to the whole pass — plus the oracle on a sample of queries."""
+    from vitrerank.engine import OTParams
+    g = synth.make_named("cars196", seed=0)
+    n, k = g.patches.shape[0], 100
+    p = OTParams(mode="rollout")
+    eng.register(g.patches, g.centers, g.rollout, g.labels)
+    kp = max(k, eng.bank["max_num_pos"], 8)
+    idx, approx = eng.stage0_topk(kp)
+    score, niter = eng.rerank_scores(idx, k, p)
+    tal, _ = eng.finalize(idx, approx, score, k, [0, k])
+    idx_h, approx_h = idx.cpu().numpy(), approx.cpu().numpy()
+    # shortlists: sorted by score, no duplicates, never the query itself
+    assert (np.diff(approx_h, axis=1) <= 0).all()
+    assert (np.sort(idx_h, axis=1)[:, 1:] != np.sort(idx_h, axis=1)[:, :-1]).all()
+    assert (idx_h != np.arange(n)[:, None]).all() and idx_h.min() >= 0 and idx_h.max() < n
+    assert torch.isfinite(score).all() and int(niter.min()) >= 1 and int(niter.max()) <= 100
+    # repeat: bit-identical
+    idx2, approx2 = eng.stage0_topk(kp)
+    score2, niter2 = eng.rerank_scores(idx2, k, p)
+    assert torch.equal(idx, idx2) and torch.equal(approx, approx2)
+    assert torch.equal(score, score2) and torch.equal(niter, niter2)
+    # whole pass = sum of three interleaved query shards; trunc 0 is the first stage alone
+    whole = eng.evaluate([0, k], p)
+    np.testing.assert_allclose(whole, tal.cpu().numpy(), rtol=1e-12)
+    parts = sum(eng.evaluate([0, k], p, q_start=s, q_stride=3) for s in range(3))
+    np.testing.assert_allclose(parts, whole, rtol=1e-12)
+    assert whole[0, 7] == n and whole[1, 7] == n
+    labels = g.labels.numpy()
+    assert whole[0, 0] == float((labels[idx_h[:, 0]] == labels).sum())     # R@1 of the global ranking
+    # oracle on a sample of queries: shortlist sets, iteration counts, per-pair scores
+    ids = list(range(5, n, n // 12))[:12]
+    ref0 = O.evaluate_banks(g.patches, g.centers, g.rollout, g.labels, trunc_nums=[0, k], use_rollout=True, ot_part=1.0,
+                            query_ids=ids, dump=True)
+    nit = niter.cpu().numpy()
+    for q, d in zip(ids, ref0["dump"]):
+        assert stop_ok(int(nit[q]), d["n_iter"], d["errs"]), (q, int(nit[q]), d["n_iter"], d["errs"][-3:])
+    ref = O.evaluate_banks(g.patches, g.centers, g.rollout, g.labels, trunc_nums=[0, k], use_rollout=True, ot_part=1.0,
+                           query_ids=ids, dump=True, force_iters=nit[ids])
+    sc = score.cpu().numpy()
+    for q, d in zip(ids, ref["dump"]):
+        assert set(idx_h[q, :k].tolist()) == set(d["top"].tolist())
+        pos = {int(c): i for i, c in enumerate(idx_h[q, :k])}
+        mine = np.array([sc[q, pos[int(c)]] for c in d["top"]])
+        assert rel_err(mine, d["score"].numpy()).max() < SCORE_RTOL
