@@ -59,8 +59,8 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&d_score, (size_t)nq * k * 4));
     CK(cudaMalloc(&d_cand, cand.size() * 4));
     CK(cudaMalloc(&d_niter, nq * 4));
-    CK(cudaMalloc(&d_clk, (size_t)nq * 16 * 8));
-    CK(cudaMemset(d_clk, 0, (size_t)nq * 16 * 8));
+    CK(cudaMalloc(&d_clk, (size_t)nq * (16 + 28) * 8));
+    CK(cudaMemset(d_clk, 0, (size_t)nq * (16 + 28) * 8));
     CK(cudaMemcpy(d_bank, bank.data(), bank.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_roll, roll.data(), roll.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_cand, cand.data(), cand.size() * 4, cudaMemcpyHostToDevice));
@@ -105,6 +105,28 @@ int main(int argc, char** argv) {
     printf("n=%d nq=%d k=%d: %.3f ms, %.2f M pairs/s, %.2f us/query/cluster-slot (%d clusters), mean n*=%.1f, score checksum %.6f\n", n, nq, k,
            best, (double)nq * k / best / 1e3, best * 1e3 * mc / nq, mc, mi, cs);
 #ifdef PR_TIMING
+#ifdef PR_SKEW
+    {
+        std::vector<long long> sk((size_t)nq * 28);
+        CK(cudaMemcpy(sk.data(), d_clk + (size_t)nq * 16, sk.size() * 8, cudaMemcpyDeviceToHost));
+        double sp[3] = {0, 0, 0}, pro = 0, lp = 0;
+        double late[7] = {0};
+        for (int q = 0; q < nq; q++)
+            for (int e = 0; e < 3; e++) {
+                long long lo = 1ll << 62, hi = 0; int arg = 0;
+                for (int r = 0; r < 7; r++) { long long t = sk[((size_t)q * 7 + r) * 4 + e]; lo = std::min(lo, t); if (t > hi) { hi = t; arg = r; } }
+                sp[e] += (double)(hi - lo);
+                if (e == 1) late[arg] += 1;
+            }
+        for (int q = 0; q < nq; q++)
+            for (int r = 0; r < 7; r++) { pro += (double)(sk[((size_t)q * 7 + r) * 4 + 1] - sk[((size_t)q * 7 + r) * 4 + 0]); lp += (double)(sk[((size_t)q * 7 + r) * 4 + 2] - sk[((size_t)q * 7 + r) * 4 + 1]); }
+        printf("  skew over the 7 CTAs of a query (ns, max - min): start %.0f, loop entry %.0f, loop exit %.0f; mean prologue %.0f ns, loop %.0f ns\n",
+               sp[0] / nq, sp[1] / nq, sp[2] / nq, pro / nq / 7, lp / nq / 7);
+        printf("  last CTA at loop entry by rank:");
+        for (int r = 0; r < 7; r++) printf(" %.1f%%", 100 * late[r] / nq);
+        printf("\n");
+    }
+#endif
     std::vector<long long> clk((size_t)nq * 16);
     CK(cudaMemcpy(clk.data(), d_clk, clk.size() * 8, cudaMemcpyDeviceToHost));
     const char* names[7] = {"cluster.sync", "S2+S3", "gibbs+K^T+TMEM", "marginals", "sinkhorn loop", "drain+dealloc", "score"};
