@@ -14,6 +14,10 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # The oracle works on 49 x 49 matrices: intra-op threading only adds synchronisation (on a busy host the 8-thread run
+    # of test_query_loop took 70 s against 2 s single-threaded); results do not depend on the thread count.
+    import torch
+    torch.set_num_threads(1)
 
 
 def pytest_collection_modifyitems(config, items):
