@@ -319,6 +319,10 @@ __global__ void __launch_bounds__(S0_THREADS, 2) stage0_scores_kernel(Stage0Args
 
 // One warp per row of the score chunk: self mask (eval_cvt_diml.py:327), streaming top-kp select with a running
 // threshold (survivors go to a P-key buffer that is re-sorted when 64 more might not fit), final sort, write-out.
+// M > 0 (kp <= 32 M): a first pass over the row keeps the M best scores of every lane in registers; the smallest of those
+// 32 M values is a lower bound of the kp-th best score, so the second pass starts with that threshold and the buffer
+// normally fills once (~1.5 kp survivors) instead of being re-sorted ~6 times while the threshold climbs from zero.
+template <int M>
 __global__ void stage0_rowselect_kernel(Stage0Args a, int64_t r_begin, int64_t rows, const float* __restrict__ scores, int64_t ld) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -334,6 +338,44 @@ __global__ void stage0_rowselect_kernel(Stage0Args a, int64_t r_begin, int64_t r
     unsigned long long thr = 0ull;
     int cnt = 0;
     const unsigned lt = (1u << lane) - 1u;
+    if (M > 0) {
+        uint32_t top[M > 0 ? M : 1];   // this lane's best ordered scores, descending
+#pragma unroll
+        for (int i = 0; i < M; i++) top[i] = 0u;
+        auto load4p = [&](float2 (&d)[4], int64_t base) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int64_t col0 = base + 64 * u + 2 * lane;
+                d[u] = make_float2(0.f, 0.f);
+                if (col0 < ld) d[u] = *reinterpret_cast<const float2*>(srow + col0);   // (kept in L2 for the second pass)
+            }
+        };
+        float2 cur[4], nxt[4];
+        load4p(cur, 0);
+        for (int64_t base = 0; base < a.n; base += 256) {
+            if (base + 256 < a.n) load4p(nxt, base + 256);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+#pragma unroll
+                for (int t = 0; t < 2; t++) {
+                    const int64_t col = base + 64 * u + 2 * lane + t;
+                    float s = t ? cur[u].y : cur[u].x;
+                    if (col == self) s = -100.0f;
+                    uint32_t o = col < a.n ? ordered_bits(s) : 0u;
+                    if (o > top[M - 1]) {
+#pragma unroll
+                        for (int i = 0; i < M; i++)
+                            if (o > top[i]) { const uint32_t x = top[i]; top[i] = o; o = x; }
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) cur[u] = nxt[u];
+        }
+        const uint32_t t0 = __reduce_min_sync(0xffffffffu, top[M - 1]);   // at least 32 M >= kp scores are >= t0
+        const unsigned long long t0key = (unsigned long long)t0 << 32;     // the smallest key with that score
+        thr = t0key ? t0key - 1ull : 0ull;                                // pass 2 keeps key > thr, i.e. key >= t0key
+    }
     // 256 scores per step, as four groups of 64 (the buffer check is per group); the next step's loads are in flight
     // while this one is filtered, so the L2 / HBM latency is paid once per row, not once per group
     auto load4 = [&](float2 (&d)[4], int64_t base) {
@@ -533,7 +575,11 @@ int stage0_topk(const float* q_centers, const int64_t* self_idx, const float* ce
         float* scores = reinterpret_cast<float*>(ws);
         const size_t smem_g = (size_t)S0_STAGES * (S0G_BM + S0_BN) * S0_LD * 4;
         VR_CHECK_CUDA(cudaFuncSetAttribute(stage0_scores_kernel<16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-        VR_CHECK_CUDA(cudaFuncSetAttribute(stage0_rowselect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gp.smem_sel));
+        // the pre-pass reads every row twice: worth it while the rows in flight (one per resident warp) come back from L2,
+        // not for SOP-sized rows of 242 KB (measured: Cars196 1.06 -> 0.80 ms, SOP 34.8 -> 37.0 ms)
+        const int selM = n > 16384 ? 0 : kp <= 128 ? 4 : kp <= 256 ? 8 : 0;
+        auto* selk = selM == 4 ? stage0_rowselect_kernel<4> : selM == 8 ? stage0_rowselect_kernel<8> : stage0_rowselect_kernel<0>;
+        VR_CHECK_CUDA(cudaFuncSetAttribute(selk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gp.smem_sel));
         const int64_t tiles_total = (n + S0_BN - 1) / S0_BN;
         for (int64_t r0 = 0; r0 < nq; r0 += gp.rows) {
             const int64_t rows = std::min(gp.rows, nq - r0);
@@ -545,7 +591,7 @@ int stage0_topk(const float* q_centers, const int64_t* self_idx, const float* ce
             dim3 grid((unsigned)groups, (unsigned)row_blocks);
             stage0_scores_kernel<16, 16><<<grid, S0_THREADS, smem_g, st>>>(a, r0, rows, tiles_per, scores, gp.ld);
             VR_LAUNCH_CHECK();
-            stage0_rowselect_kernel<<<(unsigned)((rows + gp.warps - 1) / gp.warps), gp.warps * 32, gp.smem_sel, st>>>(a, r0, rows, scores, gp.ld);
+            selk<<<(unsigned)((rows + gp.warps - 1) / gp.warps), gp.warps * 32, gp.smem_sel, st>>>(a, r0, rows, scores, gp.ld);
             VR_LAUNCH_CHECK();
         }
         return VR_OK;
