@@ -149,6 +149,41 @@ def test_calc_similarity_fused(eng, mode, kw, k, sigma):
     np.testing.assert_allclose(uv[3].cpu(), ref_uv[3], rtol=2e-4, atol=1e-8)
 
 
+@pytest.mark.parametrize("k", [100, 37, 130])
+def test_stop_test_thresholds_and_iteration_caps(eng, k):
+    """The stop test runs two iterations late on fixed-point sums whose format follows thresh * K * 49: thresholds over
+    nine decades and iteration caps around the lag (1, 2, 3) must give the iteration count the oracle's err trace
+    dictates, and the scores of exactly that many iterations."""
+    g = synth.make_gallery(k + 1, 128, 49, classes=3, seed=4242 + k, sigma=0.6)
+    _, _, (_, errs) = _oracle_pair(g, "rollout", force_iters=60)       # err of iterations 1..60, no stop
+
+    def expected(thresh, max_iter):
+        for t in range(min(max_iter, 60)):
+            if errs[t] < thresh:
+                return t + 1
+        return max_iter
+
+    cases = [(1e9, 100), (1e3, 100), (10.0, 100), (1.0, 100), (0.3, 100), (0.1, 100), (1e-2, 60), (0.0, 12),
+             (0.0, 1), (0.0, 2), (0.0, 3), (1e9, 1), (1e9, 2), (10.0, 2), (10.0, 3)]
+    for thresh, max_iter in cases:
+        p = params(mode="rollout", thresh=thresh, max_iter=max_iter)
+        score, uv, niter = eng.calc_similarity(g.patches[0], g.centers[0], g.patches[1:], g.centers[1:], p,
+                                               q_rollout=g.rollout[0], c_rollout=g.rollout[1:])
+        n_exp = expected(thresh, max_iter)
+        n_got = int(niter)
+        if n_got != n_exp:   # only legal one iteration off, at a near tie of err and thresh
+            assert abs(n_got - n_exp) == 1, (thresh, max_iter, n_got, n_exp)
+            e = errs[min(n_got, n_exp) - 1]
+            assert abs(e - thresh) <= 0.02 * thresh, (thresh, max_iter, n_got, n_exp, e)
+        ref_score, _, _ = _oracle_pair(g, "rollout", force_iters=n_got)
+        assert rel_err(score.cpu(), ref_score).max() < SCORE_RTOL, (thresh, max_iter, n_got)
+        # the score-only kernel (evaluate path) takes the same decision
+        eng.register(g.patches, g.centers, g.rollout, g.labels)
+        idx = torch.arange(1, k + 1, dtype=torch.int32, device="cuda")[None, :]
+        s2, n2 = eng.rerank_scores(idx, k, p, q_start=0, q_stride=1)
+        assert int(n2[0]) == n_got and rel_err(s2[0].cpu(), ref_score).max() < SCORE_RTOL
+
+
 @pytest.mark.parametrize("case", CALC_CASES, ids=[c[0] for c in CALC_CASES])
 def test_golden_calc_similarity(eng, golden_dir, case):
     """CUDA path against outputs of the REAL reference (tests/golden/calc_similarity.npz)."""
