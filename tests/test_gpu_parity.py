@@ -311,6 +311,7 @@ def test_evaluate_matches_oracle(eng, n, classes, seed, sigma, truncs, flags):
     (300, 128, dict(use_rollout=True, ot_part=1.0), 10),
     (560, 500, dict(use_inverse=True, temperature=0.1, use_cls_token=True, ot_part=1.0), 6),
     (1040, 1024, dict(use_rollout=True, ot_part=1.0), 3),
+    (1120, 1100, dict(use_rollout=True, ot_part=1.0), 2),      # beyond the 64-CTA groups: generic solver
 ])
 def test_wide_shortlists_fused(eng, n, k, flags, nq):
     """113..1,024 candidates per query: ceil(K / 16) CTAs per query with the CTA-level exchange.  Per-pair scores,
