@@ -1,21 +1,26 @@
 #!/usr/bin/env python
 """Benchmark of the DIML rerank hot path (BASELINE.json metric: reranked query-candidate
-pairs/s at K=100).
+pairs/s at K=100, 1/2/4/8 B200).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
 A "step" is one full pass of the hot path: every gallery image is a query, the first stage
-shortlists K'=max(K, max num_pos) candidates, K=100 of them are reranked with Sinkhorn OT,
-blended, re-sorted and tallied into r1 / RP / MAP@R.  Default workload = BASELINE.json
-configs[1]: Cars196 test shape (8,131 images, 7x7 patches, embed_dim 128, rollout marginals).
-With N GPUs the queries of the SAME pass are sharded (interleaved) over the ranks, the
-gallery is replicated and only the tallies are all-reduced (NCCL) -> strong scaling.
+shortlists K'=max(K, max num_pos) candidates, K of them are reranked with Sinkhorn OT, blended,
+re-sorted and tallied into r1 / RP / MAP@R.  Default workload = BASELINE.json configs[2], the SOP
+test shape (60,502 images, 7x7 patches, embed_dim 128, K = 100, rollout marginals): it is the gallery
+north_star puts the scaling target on, it fits one GPU (1.52 GB), and every N uses it, so BENCH, SCALE
+and the efficiency computed from them share one config.  --workload cars196 | cub200 | sop_k1000 |
+vitb16 select the other BASELINE configs.  With N GPUs the queries of the SAME pass are sharded
+(interleaved) over the ranks, the gallery is replicated and only the tallies are all-reduced (NCCL)
+-> strong scaling.
 
-JSON line fields follow the driver contract; `value` is measured with the banks resident in
-HBM, `e2e` through the host-buffer entry (pinned host banks -> device, tallies -> host
-inside the timed region), `roofline` is for the dominant kernel (pair_fused_kernel) from CUDA
-events around its launch inside the timed steps, `cpu_baseline` is the oracle (torch CPU
-restatement of the reference loop) timed on this box's host cores on a bounded sample.
+JSON line: `value` is measured with the banks resident in HBM (CUDA events on the launching stream);
+`e2e` through the host-buffer entry (pinned host banks -> device, tallies -> host inside the timed
+region); `roofline` (HBM) and `roofline_fp32` (useful Sinkhorn FMAs against the
+FP32 pipe, the roof that actually binds) are for the dominant kernel (pair_fused_kernel) from CUDA
+events around its launches inside the timed steps; `cpu_baseline` is the reference's own functions
+(oracle/_ref, kind "reference"; else the oracle port) on this box's host cores on a bounded sample;
+`parity` are the un-forced counters of that same sample against this run's CUDA results.
 """
 import argparse
 import json
@@ -36,40 +41,54 @@ import torch  # noqa: E402
 
 BYTES_PER_PAIR = {(128, 49): 25796, (768, 196): 605968}   # C*R*4 + C*4 + R*4
 WORKLOADS = {
-    # name: (synth shape name, K, flags, description)
-    "cars196": ("cars196", 100, dict(use_rollout=True, ot_part=1.0),
+    # name: (synth shape name, default n (None = the shape's), K, flags, description)
+    "sop": ("sop", None, 100, dict(use_rollout=True, ot_part=1.0),
+            "SOP test shape: 60502 images, C=128, R=49 (7x7), top-100 OT rerank, rollout marginals"),
+    "cars196": ("cars196", None, 100, dict(use_rollout=True, ot_part=1.0),
                 "Cars196 test shape: 8131 images, C=128, R=49 (7x7), top-100 OT rerank, rollout marginals"),
-    "cub200": ("cub200", 100, dict(use_rollout=True, ot_part=1.0),
+    "cub200": ("cub200", None, 100, dict(use_rollout=True, ot_part=1.0),
                "CUB-200 test shape: 5924 images, C=128, R=49, top-100 OT rerank, rollout marginals"),
-    "sop": ("sop", 100, dict(use_rollout=True, ot_part=1.0),
-            "SOP test shape: 60502 images, C=128, R=49, top-100 OT rerank, rollout marginals"),
-    "sop_k1000": ("sop", 1000, dict(use_inverse=True, temperature=0.1, use_cls_token=True, ot_part=1.0),
+    "sop_k1000": ("sop", None, 1000, dict(use_inverse=True, temperature=0.1, use_cls_token=True, ot_part=1.0),
                   "SOP shape, top-1000, calc_similarity + use_inverse T=0.1"),
+    "vitb16": ("sop_vitb16", 4096, 100, dict(use_rollout=True, ot_part=1.0),
+               "ViT-B/16 shape: C=768, R=196 (14x14), top-100 OT rerank, rollout marginals, 4096-image synthetic gallery"),
 }
 METRIC = "reranked query-candidate pairs/sec at K=100"
+FP32_LANES_PER_SM = 128
 
 
-def ncu_traffic(workload, pairs_per_launch):
-    """DRAM bytes of one pair_fused_kernel launch from the committed ncu --set full capture (profiles/), if it was
-    taken on this workload and launch size; None otherwise."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    try:
-        t = json.load(open(p))
-        if t["workload"] == workload and int(t["pairs_per_launch"]) == int(pairs_per_launch):
-            return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"])
-    except Exception:
-        pass
-    return None
+def static_config(workload, n, c, r, k, truncs, mode):
+    """The keys both arms print, identical by construction."""
+    return {"workload": WORKLOADS[workload][4], "name": workload, "n": n, "c": c, "r": r, "k": k,
+            "trunc_nums": list(truncs), "marginals": mode, "queries_per_step": n,
+            "l2": "inputs larger than L2 (patch bank %.0f MB, re-packed operand bank %.0f MB)" %
+                  (n * c * r * 4 / 1e6, n * 65536 / 1e6 if (c, r) == (128, 49) else 0.0)}
 
 
-def measured_peak():
+def static_traffic(workload, pairs_per_launch):
+    """DRAM bytes of one pair-kernel launch from the committed ncu --set full capture (profiles/r2_traffic.json), when it
+    was taken on this workload and launch size: a STATIC figure (ncu cannot run inside the timed bench); None otherwise."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", name)))
+            rows = t if isinstance(t, list) else [t]
+            for row in rows:
+                if row["workload"] == workload and int(row["pairs_per_launch"]) == int(pairs_per_launch):
+                    return float(row["dram_bytes_read"]) + float(row["dram_bytes_write"]), name
+        except Exception:
+            pass
+    return None, None
+
+
+def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
-            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)", float(d.get("sm_max_mhz", 1965.0))
         except Exception:
             pass
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)", 1965.0
 
 
 class ClockSampler:
@@ -93,7 +112,7 @@ class ClockSampler:
                     self.rows.append(parts)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.02)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -106,7 +125,7 @@ class ClockSampler:
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0}
         sm = [float(r[0]) for r in self.rows if r[0].replace('.', '', 1).isdigit()]
         mx = [float(r[1]) for r in self.rows if r[1].replace('.', '', 1).isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -115,57 +134,55 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def oracle_sample(gal, k, flags, budget_s, min_queries=16, seed=0):
-    """Time the oracle loop on uniformly sampled queries of the SAME workload until budget_s is spent."""
-    from oracle import rerank_oracle as O
+def cpu_sample(gal, k, flags, budget_s, procs, seed=0, max_queries=None):
+    """The reference's loop on uniformly sampled queries of the SAME workload until budget_s is spent: the reference's own
+    functions (oracle/_ref or the checkout) when present, else the oracle port.  Returns the sampled ids, the per-query
+    records and the timing."""
+    from oracle import parallel as OP
+    from oracle import ref_loader as RL
     n = gal.patches.shape[0]
-    torch.set_num_threads(os.cpu_count() or 1)
     rng = np.random.default_rng(seed)
     order = rng.permutation(n)
-    done, t0 = 0, time.perf_counter()
-    nit = []
-    batch = 8
-    while done < n:
-        q = order[done:done + batch]
-        out = O.evaluate_banks(gal.patches, gal.centers, gal.rollout, gal.labels, trunc_nums=[0, k],
-                               query_ids=q.tolist(), dump=True, **flags)
-        nit += [d["n_iter"] for d in out["dump"]]
-        done += len(q)
-        if time.perf_counter() - t0 > budget_s and done >= min_queries:
-            break
-    dt = time.perf_counter() - t0
-    return {"queries": done, "seconds": dt, "pairs_per_s": done * min(k, n - 0) / dt, "queries_per_s": done / dt,
-            "mean_niter": float(np.mean(nit)), "cores": torch.get_num_threads()}
+    if max_queries:
+        order = order[:max_queries]
+    kind = "reference" if RL.root() is not None else "port"
+    recs, dt, procs = OP.run(gal, order.tolist(), [0, k], flags, procs=procs, impl=kind, chunk=4, budget_s=budget_s)
+    return {"ids": np.array([int(x["q"]) for x in recs], dtype=np.int64), "recs": recs, "seconds": dt,
+            "queries": len(recs), "kind": kind,
+            "pairs_per_s": len(recs) * min(k, n) / dt, "cores": procs}
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path = the oracle port (the
-    reference is pure Python and cannot travel to this box; oracle/ is pinned against it by the
-    golden fixtures).  Rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores -- the unmodified
+    utilities/diml.py + evaluation/metrics.py functions driven as evaluation/eval_cvt_diml.py:316-372 drives them
+    (oracle/ref_loader.py over oracle/_ref, kind "reference"; the oracle port if that copy is missing, kind "port"),
+    one single-threaded worker process per core, each step a bounded sample of the workload.  Rank 0 only."""
     if rank != 0:
         return
     from vitrerank import synth
-    shape, k, flags, desc = WORKLOADS[args.workload]
-    gal = synth.make_named(shape, seed=0)
-    n = gal.patches.shape[0]
+    from vitrerank.engine import OTParams
+    shape, n_default, k, flags, desc = WORKLOADS[args.workload]
+    gal = synth.make_named(shape, seed=0, n=args.n or n_default)
+    n, c, r = gal.shape
     per_step_budget = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
-    for _ in range(args.warmup):
-        oracle_sample(gal, k, flags, per_step_budget / 4, min_queries=4, seed=99)
-    res = [oracle_sample(gal, k, flags, per_step_budget, seed=i) for i in range(args.steps)]
-    tot_q = sum(r["queries"] for r in res)
-    tot_t = sum(r["seconds"] for r in res)
-    value = tot_q * k / tot_t
-    sample = f"{tot_q} uniformly sampled queries of {n} ({tot_q * k} pairs) over {args.steps} steps, {tot_t:.1f} s"
+    procs = os.cpu_count() or 1
+    for i in range(args.warmup):
+        cpu_sample(gal, k, flags, per_step_budget / 4, procs, seed=99 + i, max_queries=4 * procs)
+    res = [cpu_sample(gal, k, flags, per_step_budget, procs, seed=i) for i in range(args.steps)]
+    tot_q = sum(x["queries"] for x in res)
+    tot_t = sum(x["seconds"] for x in res)
+    value = tot_q * min(k, n) / tot_t
+    sample = (f"{tot_q} uniformly sampled queries of {n} ({tot_q * min(k, n)} pairs) over {args.steps} steps, "
+              f"{tot_t:.1f} s, {procs} single-threaded worker processes")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "k": k, "n": n, "queries_per_s": tot_q / tot_t,
-                   "mean_sinkhorn_iters": float(np.mean([r["mean_niter"] for r in res])),
-                   "note": "bounded sample per step; oracle port of the reference loop on host cores"},
-        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": res[0]["cores"], "kind": "port",
-                         "sample": sample},
+        "config": static_config(args.workload, n, c, r, k, [0, k], OTParams.from_flags(**flags).mode),
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": procs, "kind": res[0]["kind"], "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "detail": {"queries_per_s": tot_q / tot_t,
+                   "note": "bounded sample per step; the reference's own functions on host cores, query-parallel"},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -177,10 +194,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cars196", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="sop", choices=sorted(WORKLOADS))
     ap.add_argument("--n", type=int, default=None, help="override gallery size (debug)")
-    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of oracle time for cpu_baseline")
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of reference time for cpu_baseline")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip cpu_baseline / parity (profiling runs)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -200,8 +218,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    shape, k, flags, desc = WORKLOADS[args.workload]
-    gal = synth.make_named(shape, seed=0, n=args.n)
+    shape, n_default, k, flags, desc = WORKLOADS[args.workload]
+    gal = synth.make_named(shape, seed=0, n=args.n or n_default)
     n, c, r = gal.shape
     params = OTParams.from_flags(**flags)
     truncs = [0, k]
@@ -211,7 +229,7 @@ def main():
     nq = (n - rank + world - 1) // world           # interleaved shard: queries rank, rank+world, ...
     t_dev = torch.zeros(len(truncs), 8, dtype=torch.float64, device=dev)
 
-    def step(timers=None):
+    def step(timers=None, keep=False):
         """One pass over this rank's query shard, banks resident in HBM."""
         t_dev.zero_()
         if timers:
@@ -222,12 +240,15 @@ def main():
         score, niter = eng.rerank_scores(idx, k, params, q_start=rank, q_stride=world)
         if timers:
             timers[2].record()
-        eng.finalize(idx, approx, score, k, truncs, q_start=rank, q_stride=world, tallies=t_dev)
+        res = eng.finalize(idx, approx, score, k, truncs, q_start=rank, q_stride=world, tallies=t_dev,
+                           want_per_query=keep)
         if world > 1:
             dist.all_reduce(t_dev)                  # the path's only exchange: 16 doubles
         out = t_dev.cpu()                           # device -> host read of the tallies
         if timers:
             timers[3].record()
+        if keep:
+            return out, niter, (idx, score, res[2])
         return out, niter
 
     def sync_all():
@@ -236,7 +257,8 @@ def main():
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         tallies, niter = step()
     sync_all()
     niter_np = niter.cpu().numpy()
@@ -271,7 +293,7 @@ def main():
 
         def e2e_step():
             # world == 1: vr_evaluate_host (the C-ABI host-buffer entry).  world > 1: every image crosses PCIe once per
-            # node (this rank uploads its 1/W of the patch bank), NVLink all-gather, tallies all-reduced.
+            # node (this rank uploads its slices of the patch bank), pipelined NVLink all-gather, tallies all-reduced.
             return vdist.evaluate_host_sharded(eng, pin.patches, pin.centers, pin.rollout, pin.labels, truncs, params)
 
         for _ in range(2):
@@ -289,9 +311,10 @@ def main():
         assert np.allclose(tal_h, tallies.numpy(), rtol=0, atol=1e-9), "end-to-end tallies differ from the resident pass"
         e2e = {"value": pairs_per_step * args.steps / dt, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * dt / args.steps,
-               "note": ("vr_evaluate_host: pinned host banks -> HBM, S1..S5, tallies -> host" if world == 1 else
-                        "evaluate_host_sharded: each rank uploads 1/W of the patch bank (bytes are per rank), NVLink all-gather, "
-                        "S1..S5 on its query shard, tallies all-reduced -> host")}
+               "note": ("vr_evaluate_host: pinned host banks -> HBM in pieces (re-packed as they land), S1..S5, tallies -> host"
+                        if world == 1 else
+                        "evaluate_host_sharded: each rank uploads 1/W of the patch bank (bytes are per rank), pipelined NVLink "
+                        "all-gather + re-pack under stage 0, S1..S5 on its query shard, tallies all-reduced -> host")}
         launches_e2e = _lib.take_launch_count()
         eng.register(gal.patches, gal.centers, gal.rollout, gal.labels)
     else:
@@ -302,48 +325,77 @@ def main():
             dist.destroy_process_group()
         return
 
-    peak, peak_src = measured_peak()
+    peak, peak_src, sm_max_mhz = measured_peaks()
     bpp = BYTES_PER_PAIR.get((c, r), c * r * 4 + c * 4 + r * 4)
     pairs_per_launch = nq * min(k, n)
     achieved = pairs_per_launch * bpp / (pf_ms / 1e3) / 1e9
+    # FP32 roof: the useful work of the Sinkhorn loop is 2 * R * R FMAs per pair and iteration (two mat-vecs)
+    mean_it = float(niter_np.mean())
+    fma_per_launch = float(pairs_per_launch) * mean_it * 2.0 * r * r
+    fp32_peak = eng.sm_count * FP32_LANES_PER_SM * sm_max_mhz * 1e6 / 1e12      # TFMA/s
+    fp32_achieved = fma_per_launch / (pf_ms / 1e3) / 1e12
+    traffic, traffic_file = static_traffic(args.workload, pairs_per_launch)
     scale = n / 100.0
     line = {
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+        "warmup": warm, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "n": n, "c": c, "r": r, "k": k, "kp": kp, "trunc_nums": truncs,
-                   "marginals": params.mode, "parallelism": f"queries sharded x{world}, gallery replicated",
-                   "queries_per_s": value / min(k, n), "l2": "inputs larger than L2 (patch bank %.0f MB)" %
-                   (gal.patches.numel() * 4 / 1e6),
-                   "sinkhorn_iters": {"mean": float(niter_np.mean()), "min": int(niter_np.min()),
-                                      "max": int(niter_np.max())},
-                   "stage_ms": {"stage0_topk": s0_ms, "pair_fused": pf_ms, "finalize_tally_d2h": fin_ms},
+        "config": static_config(args.workload, n, c, r, k, truncs, params.mode),
+        "detail": {"kp": kp, "parallelism": f"queries sharded x{world}, gallery replicated",
+                   "queries_per_s": value / min(k, n),
+                   "sinkhorn_iters": {"mean": mean_it, "min": int(niter_np.min()), "max": int(niter_np.max())},
+                   "stage_ms": {"stage0_topk": s0_ms, "pair_kernel": pf_ms, "finalize_tally_d2h": fin_ms},
                    "metrics": {"r1": (tallies[:, 0] / scale).tolist(), "rp": (tallies[:, 1] / scale).tolist(),
                                "mapr": (tallies[:, 2] / scale).tolist()},
                    "sm_count": eng.sm_count, "pair_transport": os.environ.get("VR_PAIR_TRANSPORT", "global")},
         "roofline": {"bound": "hbm", "kernel": "pair_fused_kernel", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.workload, pairs_per_launch),
-                     "traffic_unit": "bytes per launch (dram read + write, ncu)", "peak_source": peak_src,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "traffic_source": (f"static: ncu --set full capture of this workload and launch size, profiles/{traffic_file}"
+                                        if traffic is not None else None),
+                     "traffic_unit": "bytes per launch (dram read + write)", "peak_source": peak_src,
                      "algorithmic_bytes_per_pair": bpp, "pairs_per_launch": pairs_per_launch,
                      "kernel_ms": pf_ms, "kernel_share_of_step": pf_ms / (elapsed_ms / args.steps),
-                     "note": "the gather is the only unavoidable HBM traffic, but the kernel is bound by FP32 issue / latency "
-                             "in the Sinkhorn loop (see DESIGN.md section 3): frac is low by construction"},
+                     "note": "the candidate gather is the only unavoidable HBM traffic (SURVEY 8d); the kernel is bound by "
+                             "FP32 issue / latency in the Sinkhorn loop, see roofline_fp32"},
+        "roofline_fp32": {"bound": "fp32", "kernel": "pair_fused_kernel", "achieved": fp32_achieved, "peak": fp32_peak,
+                          "unit": "TFMA/s", "frac": fp32_achieved / fp32_peak,
+                          "useful_fma_per_pair_iteration": 2 * r * r, "mean_iterations": mean_it,
+                          "peak_source": f"{eng.sm_count} SMs x {FP32_LANES_PER_SM} FP32 lanes x {sm_max_mhz:.0f} MHz"},
         "clocks": clocks.summary(),
         "gpu_launches": int(launches),
     }
     if e2e:
         line["e2e"] = e2e
         line["gpu_launches_e2e"] = int(launches_e2e)
-    # ---- CPU baseline: the oracle on this box's host cores, bounded sample ----
+    # ---- CPU baseline + parity counters: the reference on this box's host cores, bounded sample ----
     if world > 1:
         dist.destroy_process_group()
-    if world == 1:
-        base = oracle_sample(gal, k, flags, args.cpu_budget)
-        line["cpu_baseline"] = {"value": base["pairs_per_s"], "unit": "pairs/s", "cores": base["cores"],
-                                "kind": "port",
-                                "sample": f"{base['queries']} uniformly sampled queries of {n} "
-                                          f"({base['queries'] * k} pairs), {base['seconds']:.1f} s, mean n*="
-                                          f"{base['mean_niter']:.1f}"}
+    if world == 1 and not args.no_cpu:
+        from oracle import parity as PAR
+        tallies, niter, (idx, score, per_q) = step(keep=True)
+        torch.cuda.synchronize(dev)
+        procs = os.cpu_count() or 1
+        base = cpu_sample(gal, k, flags, args.cpu_budget, procs)
+        one = cpu_sample(gal, k, flags, max(3.0, args.cpu_budget / 3), 1, seed=1)
+        line["cpu_baseline"] = {
+            "value": base["pairs_per_s"], "unit": "pairs/s", "cores": base["cores"], "kind": base["kind"],
+            "sample": f"{base['queries']} uniformly sampled queries of {n} ({base['queries'] * min(k, n)} pairs), "
+                      f"{base['seconds']:.1f} s, {base['cores']} single-threaded worker processes",
+            "one_thread": {"value": one["pairs_per_s"], "unit": "pairs/s", "cores": 1,
+                           "sample": f"{one['queries']} queries, {one['seconds']:.1f} s"}}
+        # parity of the same sample, un-forced.  The reference's functions expose neither iteration counts nor err traces:
+        # those counters come from the oracle port on the same queries (bit-identical scores, tests/test_oracle_golden.py)
+        from oracle import parallel as OP
+        ids = base["ids"][:min(len(base["ids"]), 256)]
+        dumps, _, _ = OP.run(gal, ids.tolist(), truncs, flags, procs=procs, impl="port", chunk=4)
+        ids_t = torch.as_tensor(ids, device=dev, dtype=torch.long)
+        par = PAR.compare(dumps, idx[ids_t].cpu().numpy(), score[ids_t].cpu().numpy(), niter[ids_t].cpu().numpy(), k,
+                          trunc_nums=truncs, per_query=per_q[ids_t].cpu().numpy())
+        if base["kind"] == "reference":   # scores of the REAL functions against the port on the sample: must be identical
+            par["reference_vs_port_score_mismatches"] = int(sum(
+                0 if torch.equal(a["score"], b["score"]) else 1 for a, b in zip(base["recs"][:len(dumps)], dumps)))
+        par["sample"] = f"{len(dumps)} of the cpu_baseline queries, compared un-forced (oracle keeps its iteration counts)"
+        line["parity"] = par
     print(json.dumps(line), flush=True)
 
 

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define VR_ABI_VERSION 1
+#define VR_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define VR_API __attribute__((visibility("default")))
@@ -90,6 +90,19 @@ VR_API int vr_device_info(vr_ctx* ctx, int32_t* sm_count, int32_t* max_active_cl
  * on that call's stream); register again after modifying a registered bank in place. */
 VR_API int vr_bank_register(vr_ctx* ctx, const float* patches, const float* centers, const float* rollout,
                      const int64_t* labels, const int32_t* num_pos, int64_t n, int32_t c, int32_t r);
+
+/* Derives the library-owned operand copy of images [first, first + count) of the registered bank now, on `stream`
+ * (ranges in ascending order without gaps; once [0, n) is covered the fused rerank uses the copy as it is).  Lets a caller
+ * that fills the bank piecewise (uploads, all-gathers) overlap the re-pack with the transfers and with stage 0; later
+ * rerank calls must be ordered after it by the caller (same stream or an event).  No-op for shapes without a fused kernel. */
+VR_API int vr_bank_prepare(vr_ctx* ctx, int64_t first, int64_t count, void* stream);
+
+/* num_pos[i] = #{j : labels[j] == labels[i]}: the `num_pos = torch.sum(gallery_label == query_label)` of
+ * evaluation/metrics.py:34 for every gallery item at once (device int32 [n]; counts the item itself).  When
+ * max_num_pos_host is not NULL the call synchronises `stream` and stores the largest count there (the first-stage
+ * shortlist must be at least that long, see vr_finalize). */
+VR_API int vr_num_pos(vr_ctx* ctx, const int64_t* labels, int64_t n, int32_t* num_pos, int32_t* max_num_pos_host,
+                      void* stream);
 
 /* S1: first-stage retrieval -----------------------------------------------------------
  * Replaces, for a batch of queries, calc_similarity(stage=0) (diml.py:83-85), the self

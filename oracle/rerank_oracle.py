@@ -258,14 +258,18 @@ def evaluate_banks(patches, centers, rollout, labels, trunc_nums=None, use_rollo
             total = score + approx[top]
             rank = torch.argsort(total, descending=True, stable=True)
             if dump:
+                # gap: distance between the last shortlisted score and the first one left out (stage-0 boundary)
+                gap = float(approx[top[-1]] - approx[approx_tops[kmax]]) if kmax < n else float("inf")
                 rec.update(top=top.clone(), approx=approx[top].clone(), score=score.clone(),
-                           total=total.clone(), rank=rank.clone(), n_iter=n_iter, errs=errs)
+                           total=total.clone(), rank=rank.clone(), n_iter=n_iter, errs=errs, gap=gap)
+        rec["metrics"] = {}
         for t in trunc_nums:
             if t == 0:
                 final = approx_tops
             else:
                 final = torch.cat([top[rank][:t], approx_tops[t:]], dim=0)
             r1, rp, mapr = metrics_rank(final, labels[idx], labels)
+            rec["metrics"][t] = (r1, rp, mapr)
             s = sums[t]
             s[0] += r1
             s[1] += rp

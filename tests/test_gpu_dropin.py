@@ -50,23 +50,17 @@ def test_calc_similarity_dropin_vs_reference_outputs(golden_dir, case):
                                                     use_cls_token=kw.get("use_cls_token", False),
                                                     ot_part=kw.get("ot_part", 1.0), trace=True)
     assert n_ref == int(G[f"{name}_meta"][3])
+    # un-forced, against the outputs of the REAL reference: a borderline stop may leave the CUDA path one iteration apart
+    # (which iteration count it ran is visible through the plan: T of n and n +- 1 iterations differ by > 2e-4 somewhere)
     close_T = np.allclose(uv[2].cpu().numpy(), G[f"{name}_T"], rtol=2e-4, atol=1e-9)
-    if not close_T:   # one iteration off at a borderline stop: compare at equal counts instead
-        ok = False
-        for n_try in (n_ref - 1, n_ref + 1):
-            if n_try >= 1 and stop_ok(n_try, n_ref, errs):
-                s2, uv2, _ = O.structural_similarity(gc.patches[0], gc.centers[0], gc.patches[1:], gc.centers[1:], mode,
-                                                     ot_temp=kw.get("ot_temp", 0.05),
-                                                     temperature=kw.get("temperature", 1.0),
-                                                     use_cls_token=kw.get("use_cls_token", False),
-                                                     ot_part=kw.get("ot_part", 1.0), trace=True, force_iters=n_try)
-                if np.allclose(uv[2].cpu().numpy(), uv2[2].numpy(), rtol=2e-4, atol=1e-9):
-                    assert rel_err(score.cpu(), s2).max() < 1e-4
-                    ok = True
-        assert ok, "plan differs from the reference beyond a borderline stop"
-    else:
+    if close_T:
         assert rel_err(score.cpu(), G[f"{name}_score"]).max() < 1e-4
         np.testing.assert_allclose(uv[3].cpu(), G[f"{name}_simr"], rtol=2e-4, atol=1e-8)
+    else:
+        assert any(stop_ok(n_try, n_ref, errs) for n_try in (n_ref - 1, n_ref + 1) if n_try >= 1), \
+            "plan differs from the reference although its stop was not borderline"
+        assert rel_err(score.cpu(), G[f"{name}_score"]).max() < 5e-4
+        np.testing.assert_allclose(uv[2].cpu(), G[f"{name}_T"], rtol=2e-2, atol=1e-9)
 
 
 def test_stage0_and_rollout_dropin(golden_dir):
@@ -178,9 +172,12 @@ def test_evaluate_entry_point_with_stub_model(flags, capsys):
     nit = extra["sinkhorn_iters"]
     cpu = [t.cpu() if t is not None else None for t in (patches, centers, rollout, labels)]
     ref = O.evaluate_banks(*cpu, trunc_nums=truncs, dump=True, **oflags)
+    flips = 0
     for q, d in enumerate(ref["dump"]):
-        assert abs(int(nit[q]) - d["n_iter"]) <= 1
-    if any(int(nit[q]) != d["n_iter"] for q, d in enumerate(ref["dump"])):
-        ref = O.evaluate_banks(*cpu, trunc_nums=truncs, force_iters=nit, **oflags)
-    for key in ("r1", "rp", "mapr"):
-        np.testing.assert_allclose(data[key], ref[key], rtol=1e-6, atol=1e-6)
+        assert stop_ok(int(nit[q]), d["n_iter"], d["errs"])
+        flips += int(nit[q]) != d["n_iter"]
+    for key in ("r1", "rp", "mapr"):   # un-forced: identical unless a borderline stop moved a query (<= 100/n each)
+        if flips == 0:
+            assert list(data[key]) == list(ref[key]), (key, data[key], ref[key])
+        else:
+            np.testing.assert_allclose(data[key], ref[key], rtol=0, atol=flips * 100.0 / 160 + 1e-9)

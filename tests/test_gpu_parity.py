@@ -18,7 +18,18 @@ from golden.cases import CALC_CASES, LOOP_CASES
 
 pytestmark = pytest.mark.gpu
 
-SCORE_RTOL = 1e-4
+SCORE_RTOL = 1e-4    # north_star gate: per-pair OT scores within 1e-4 relative (queries with the reference's iteration count)
+FLIP_RTOL = 5e-4     # a query one Sinkhorn iteration apart from the oracle is compared UN-FORCED: SURVEY.md section 7 measured
+                     # up to 1.3e-4 for such an off-by-one; tests/test_gpu_fullpass.py counts them at full size
+
+
+def score_gate(n_mine, n_ref):
+    return SCORE_RTOL if int(n_mine) == int(n_ref) else FLIP_RTOL
+
+
+def plan_tol(n_mine, n_ref):
+    """rtol for the transport plan T / sim_r against the un-forced oracle."""
+    return 2e-4 if int(n_mine) == int(n_ref) else 2e-2
 
 
 @pytest.fixture(scope="module")
@@ -142,11 +153,10 @@ def test_calc_similarity_fused(eng, mode, kw, k, sigma):
     if ref_uv[4] is not None:
         np.testing.assert_allclose(uv[4].cpu(), ref_uv[4], rtol=1e-5, atol=2e-6)
     assert stop_ok(int(niter), n_ref, errs), f"n* {int(niter)} vs oracle {n_ref}, errs tail {errs[-3:]}"
-    if int(niter) != n_ref:  # compare at equal iteration counts
-        ref_score, ref_uv, _ = _oracle_pair(g, mode, force_iters=int(niter), **kw)
-    assert rel_err(score.cpu(), ref_score).max() < SCORE_RTOL
-    np.testing.assert_allclose(uv[2].cpu(), ref_uv[2], rtol=2e-4, atol=1e-9)
-    np.testing.assert_allclose(uv[3].cpu(), ref_uv[3], rtol=2e-4, atol=1e-8)
+    # un-forced: the oracle keeps ITS iteration count
+    assert rel_err(score.cpu(), ref_score).max() < score_gate(niter, n_ref)
+    np.testing.assert_allclose(uv[2].cpu(), ref_uv[2], rtol=plan_tol(niter, n_ref), atol=1e-9)
+    np.testing.assert_allclose(uv[3].cpu(), ref_uv[3], rtol=plan_tol(niter, n_ref), atol=1e-8)
 
 
 @pytest.mark.parametrize("k", [100, 37, 130])
@@ -175,13 +185,16 @@ def test_stop_test_thresholds_and_iteration_caps(eng, k):
             assert abs(n_got - n_exp) == 1, (thresh, max_iter, n_got, n_exp)
             e = errs[min(n_got, n_exp) - 1]
             assert abs(e - thresh) <= 0.02 * thresh, (thresh, max_iter, n_got, n_exp, e)
-        ref_score, _, _ = _oracle_pair(g, "rollout", force_iters=n_got)
-        assert rel_err(score.cpu(), ref_score).max() < SCORE_RTOL, (thresh, max_iter, n_got)
+        # the reference has one threshold (0.1) and one cap (100); other values exist only through the oracle's
+        # err trace, so its result is the run of exactly n_exp iterations -- the count ITS trace dictates
+        ref_score, _, _ = _oracle_pair(g, "rollout", force_iters=n_exp)
+        if n_got == n_exp:
+            assert rel_err(score.cpu(), ref_score).max() < SCORE_RTOL, (thresh, max_iter, n_got, n_exp)
         # the score-only kernel (evaluate path) takes the same decision
         eng.register(g.patches, g.centers, g.rollout, g.labels)
         idx = torch.arange(1, k + 1, dtype=torch.int32, device="cuda")[None, :]
         s2, n2 = eng.rerank_scores(idx, k, p, q_start=0, q_stride=1)
-        assert int(n2[0]) == n_got and rel_err(s2[0].cpu(), ref_score).max() < SCORE_RTOL
+        assert int(n2[0]) == n_got and torch.equal(s2[0].cpu(), score.cpu())
 
 
 @pytest.mark.parametrize("case", CALC_CASES, ids=[c[0] for c in CALC_CASES])
@@ -196,15 +209,14 @@ def test_golden_calc_similarity(eng, golden_dir, case):
                ot_temp=kw.get("ot_temp", 0.05), ot_part=kw.get("ot_part", 1.0))
     score, uv, niter = eng.calc_similarity(g.patches[0], g.centers[0], g.patches[1:], g.centers[1:], p)
     n_ref = int(G[f"{name}_meta"][3])
-    if int(niter) != n_ref:
+    if int(niter) != n_ref:   # legal only at a borderline stop; the comparison below stays against the reference's output
         _, _, (n_o, errs) = O.structural_similarity(g.patches[0], g.centers[0], g.patches[1:], g.centers[1:], mode,
                                                     ot_temp=p.ot_temp, temperature=p.temperature,
                                                     use_cls_token=p.use_cls_token, ot_part=p.ot_part, trace=True)
-        assert n_o == n_ref and stop_ok(int(niter), n_ref, errs)
-        pytest.skip(f"stop test within 2% of the threshold: n* {int(niter)} vs reference {n_ref}")
-    assert rel_err(score.cpu(), G[f"{name}_score"]).max() < SCORE_RTOL
-    np.testing.assert_allclose(uv[2].cpu(), G[f"{name}_T"], rtol=2e-4, atol=1e-9)
-    np.testing.assert_allclose(uv[3].cpu(), G[f"{name}_simr"], rtol=2e-4, atol=1e-8)
+        assert stop_ok(int(niter), n_o, errs), (int(niter), n_o, n_ref)
+    assert rel_err(score.cpu(), G[f"{name}_score"]).max() < score_gate(niter, n_ref)
+    np.testing.assert_allclose(uv[2].cpu(), G[f"{name}_T"], rtol=plan_tol(niter, n_ref), atol=1e-9)
+    np.testing.assert_allclose(uv[3].cpu(), G[f"{name}_simr"], rtol=plan_tol(niter, n_ref), atol=1e-8)
 
 
 @pytest.mark.parametrize("name", ["rollout", "rollout_iid", "rollout_part", "rollout_uniform"])
@@ -223,10 +235,9 @@ def test_golden_rollout(eng, golden_dir, name):
         _, _, (n_o, errs) = O.structural_similarity(g.patches[0], g.centers[0], g.patches[1:], g.centers[1:], p.mode,
                                                     ot_part=p.ot_part, q_rollout=g.rollout[0],
                                                     c_rollout=g.rollout[1:], trace=True)
-        assert n_o == n_ref and stop_ok(int(niter), n_ref, errs)
-        pytest.skip(f"stop test within 2% of the threshold: n* {int(niter)} vs reference {n_ref}")
-    assert rel_err(score.cpu(), G[f"{name}_score"]).max() < SCORE_RTOL
-    np.testing.assert_allclose(uv[2].cpu(), G[f"{name}_T"], rtol=2e-4, atol=1e-9)
+        assert stop_ok(int(niter), n_o, errs), (int(niter), n_o, n_ref)
+    assert rel_err(score.cpu(), G[f"{name}_score"]).max() < score_gate(niter, n_ref)
+    np.testing.assert_allclose(uv[2].cpu(), G[f"{name}_T"], rtol=plan_tol(niter, n_ref), atol=1e-9)
 
 
 @pytest.mark.parametrize("name", ["a", "b", "c"])
@@ -238,20 +249,18 @@ def test_golden_sinkhorn(eng, golden_dir, name):
     u = g.rollout[1:] / (g.rollout[1:].sum(1, keepdim=True) + 1e-5)
     v = (g.rollout[0:1] / (g.rollout[0:1].sum(1, keepdim=True) + 1e-5)).expand(b, -1).contiguous()
     T, niter = eng.sinkhorn(K, u, v)
-    if int(niter) == n_ref:
-        np.testing.assert_allclose(T.cpu(), G[f"{name}_T"], rtol=2e-4, atol=1e-10)
-    else:
-        _, n_o, errs = O.sinkhorn(K, u, v, trace=True)
-        assert n_o == n_ref and stop_ok(int(niter), n_ref, errs)
-        np.testing.assert_allclose(T.cpu(), O.sinkhorn(K, u, v, force_iters=int(niter)), rtol=2e-4, atol=1e-10)
+    # given K, u, v the CUDA Sinkhorn is bit-identical to torch on THIS host (test_sinkhorn_bit_exact_given_inputs); the
+    # fixture was made on another host, whose exp() may differ in the last bit of K
+    T_here, n_here, errs = O.sinkhorn(K, u, v, trace=True)
+    assert int(niter) == n_here and torch.equal(T.cpu(), T_here)
+    assert stop_ok(n_here, n_ref, errs)
+    np.testing.assert_allclose(T.cpu(), G[f"{name}_T"], rtol=plan_tol(niter, n_ref), atol=1e-10)
     Ke, ue, ve = O.partial_extend(K, u, v, 0.5)
     Te, niter = eng.sinkhorn(Ke, ue, ve)
     n_refp = int(G[f"{name}_npartial"][0])
-    if int(niter) == n_refp:
-        np.testing.assert_allclose(Te.cpu(), G[f"{name}_Tpartial"], rtol=2e-4, atol=1e-10)
-    else:
-        _, n_o, errs = O.sinkhorn(Ke, ue, ve, trace=True)
-        assert n_o == n_refp and stop_ok(int(niter), n_refp, errs)
+    _, n_here, errs = O.sinkhorn(Ke, ue, ve, trace=True)
+    assert int(niter) == n_here and stop_ok(n_here, n_refp, errs)
+    np.testing.assert_allclose(Te.cpu(), G[f"{name}_Tpartial"], rtol=plan_tol(niter, n_refp), atol=1e-10)
 
 
 @pytest.mark.parametrize("c,r,k,mode,kw", [(32, 16, 9, "rollout", {}), (64, 36, 150, "rollout", {}),
@@ -267,10 +276,8 @@ def test_generic_path(eng, c, r, k, mode, kw):
                                            params(mode=mode, **kw), q_rollout=g.rollout[0],
                                            c_rollout=g.rollout[1:])
     assert stop_ok(int(niter), n_ref, errs), f"n* {int(niter)} vs oracle {n_ref}, errs tail {errs[-3:]}"
-    if int(niter) != n_ref:
-        ref_score, ref_uv, _ = _oracle_pair(g, mode, force_iters=int(niter), **kw)
-    assert rel_err(score.cpu(), ref_score).max() < SCORE_RTOL
-    np.testing.assert_allclose(uv[2].cpu(), ref_uv[2], rtol=2e-4, atol=1e-9)
+    assert rel_err(score.cpu(), ref_score).max() < score_gate(niter, n_ref)
+    np.testing.assert_allclose(uv[2].cpu(), ref_uv[2], rtol=plan_tol(niter, n_ref), atol=1e-9)
 
 
 EVAL_CASES = [
@@ -295,15 +302,18 @@ def test_evaluate_matches_oracle(eng, n, classes, seed, sigma, truncs, flags):
     flips = int((nit != n_ref).sum())
     for q, d in enumerate(ref["dump"]):
         assert stop_ok(int(nit[q]), d["n_iter"], d["errs"]), (q, int(nit[q]), d["n_iter"], d["errs"][-3:])
-    if flips:  # compare metrics at equal iteration counts
-        ref = O.evaluate_banks(g.patches, g.centers, g.rollout, g.labels, trunc_nums=list(truncs), force_iters=nit,
-                               **flags)
     scale = n / 100.0
     got = {"r1": tal[:, 0] / scale, "rp": tal[:, 1] / scale, "mapr": tal[:, 2] / scale}
     assert tal[0, 7] == n
+    # un-forced: identical (==) when every query ran the oracle's iteration count; a query one iteration apart may
+    # reorder near-equal totals, which moves a tally by at most 1 / scale per such query
+    slack = flips / scale
     for key in ("r1", "rp", "mapr"):
-        np.testing.assert_allclose(got[key], ref[key], rtol=1e-7, atol=1e-7)
-    np.testing.assert_allclose(tal[:, 3:7] / scale, np.array(ref["recall_at_1_2_4_8"]), rtol=1e-7, atol=1e-7)
+        if flips == 0:
+            assert (np.asarray(got[key]) == np.asarray(ref[key])).all(), (key, got[key], ref[key])
+        else:
+            np.testing.assert_allclose(got[key], ref[key], rtol=0, atol=slack + 1e-9)
+    np.testing.assert_allclose(tal[:, 3:7] / scale, np.array(ref["recall_at_1_2_4_8"]), rtol=0, atol=slack + 1e-9)
 
 
 @pytest.mark.parametrize("n,k,flags,nq", [
@@ -327,22 +337,20 @@ def test_wide_shortlists_fused(eng, n, k, flags, nq):
     tal, _ = eng.finalize(idx, approx, score, k, [0, k], q_start=0, q_stride=stride)
     idx, score, niter = idx.cpu().numpy(), score.cpu().numpy(), niter.cpu().numpy()
     ref0 = O.evaluate_banks(g.patches, g.centers, g.rollout, g.labels, trunc_nums=[0, k], query_ids=ids, dump=True, **flags)
+    flips = 0
     for q, d in enumerate(ref0["dump"]):
         assert stop_ok(int(niter[q]), d["n_iter"], d["errs"]), (q, int(niter[q]), d["n_iter"], d["errs"][-3:])
-    ref = O.evaluate_banks(g.patches, g.centers, g.rollout, g.labels, trunc_nums=[0, k], query_ids=ids, dump=True,
-                           force_iters=niter, **flags)
-    worst = 0.0
-    for q, d in enumerate(ref["dump"]):
+        flips += int(niter[q]) != d["n_iter"]
+    for q, d in enumerate(ref0["dump"]):   # un-forced
         assert set(idx[q].tolist()) == set(d["top"].tolist())
         pos = {int(c): i for i, c in enumerate(idx[q])}
         mine = np.array([score[q, pos[int(c)]] for c in d["top"]])
-        worst = max(worst, rel_err(mine, d["score"].numpy()).max())
-    assert worst < SCORE_RTOL, worst
+        assert rel_err(mine, d["score"].numpy()).max() < score_gate(niter[q], d["n_iter"]), q
     scale = n / 100.0
     tal = tal.cpu().numpy()
     assert tal[0, 7] == nq
     for col, key in enumerate(("r1", "rp", "mapr")):
-        np.testing.assert_allclose(tal[:, col] / scale, ref[key], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(tal[:, col] / scale, ref0[key], rtol=0, atol=flips / scale + 1e-9)
 
 
 def test_evaluate_stages_and_scores(eng):
@@ -357,22 +365,17 @@ def test_evaluate_stages_and_scores(eng):
     score, niter = eng.rerank_scores(idx, k, OTParams(mode="rollout"))
     tal, rank = eng.finalize(idx, approx, score, k, [0, k], want_rank=True)
     idx, approx, score, niter, rank = [t.cpu().numpy() for t in (idx, approx, score, niter, rank)]
-    for q, d in enumerate(ref0["dump"]):
+    for q, d in enumerate(ref0["dump"]):   # un-forced: the oracle keeps its own iteration counts
         assert stop_ok(int(niter[q]), d["n_iter"], d["errs"]), (q, int(niter[q]), d["n_iter"], d["errs"][-3:])
-    # scores and order are compared at equal iteration counts
-    ref = O.evaluate_banks(g.patches, g.centers, g.rollout, g.labels, trunc_nums=[0, k], use_rollout=True,
-                           ot_part=1.0, dump=True, force_iters=niter)
-    worst = 0.0
-    for q, d in enumerate(ref["dump"]):
         assert set(idx[q].tolist()) == set(d["top"].tolist())
         pos = {int(c): i for i, c in enumerate(idx[q])}
         mine = np.array([score[q, pos[int(c)]] for c in d["top"]])
-        worst = max(worst, rel_err(mine, d["score"].numpy()).max())
+        gate = score_gate(niter[q], d["n_iter"])
+        assert rel_err(mine, d["score"].numpy()).max() < gate, q
         ref_order = d["top"][d["rank"]].numpy()
         if not np.array_equal(rank[q], ref_order):
             tot = np.sort(d["total"].numpy())[::-1]
-            assert np.min(np.abs(np.diff(tot))) < 1e-5, f"query {q}: reranked order differs without a near tie"
-    assert worst < SCORE_RTOL, worst
+            assert np.min(np.abs(np.diff(tot))) < 10 * gate, f"query {q}: reranked order differs without a near tie"
 
 
 def test_evaluate_host_equals_device(eng):
@@ -517,7 +520,8 @@ def test_evaluate_host_sharded_two_rank_nccl(tmp_path):
         assert p.wait(timeout=300) == 0
     got = json.load(open(out))
     np.testing.assert_allclose(np.array(got["t"]), np.array(got["whole"]), rtol=1e-12)
-    assert got["h2d"] == 151 * 128 * 49 * 4 + 301 * 128 * 4 + 301 * 49 * 4 + 301 * 8
+    # 4 pieces x 2 slices of 38 images: rank 0 uploads slices 0, 2, 4, 6 = 152 images
+    assert got["h2d"] == 152 * 128 * 49 * 4 + 301 * 128 * 4 + 301 * 49 * 4 + 301 * 8
 
 
 def test_full_size_properties_cars196(eng):
@@ -558,13 +562,10 @@ def test_full_size_properties_cars196(eng):
     ref0 = O.evaluate_banks(g.patches, g.centers, g.rollout, g.labels, trunc_nums=[0, k], use_rollout=True, ot_part=1.0,
                             query_ids=ids, dump=True)
     nit = niter.cpu().numpy()
-    for q, d in zip(ids, ref0["dump"]):
-        assert stop_ok(int(nit[q]), d["n_iter"], d["errs"]), (q, int(nit[q]), d["n_iter"], d["errs"][-3:])
-    ref = O.evaluate_banks(g.patches, g.centers, g.rollout, g.labels, trunc_nums=[0, k], use_rollout=True, ot_part=1.0,
-                           query_ids=ids, dump=True, force_iters=nit[ids])
     sc = score.cpu().numpy()
-    for q, d in zip(ids, ref["dump"]):
+    for q, d in zip(ids, ref0["dump"]):    # un-forced (the whole pass is compared in tests/test_gpu_fullpass.py)
+        assert stop_ok(int(nit[q]), d["n_iter"], d["errs"]), (q, int(nit[q]), d["n_iter"], d["errs"][-3:])
         assert set(idx_h[q, :k].tolist()) == set(d["top"].tolist())
         pos = {int(c): i for i, c in enumerate(idx_h[q, :k])}
         mine = np.array([sc[q, pos[int(c)]] for c in d["top"]])
-        assert rel_err(mine, d["score"].numpy()).max() < SCORE_RTOL
+        assert rel_err(mine, d["score"].numpy()).max() < score_gate(nit[q], d["n_iter"])

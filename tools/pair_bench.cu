@@ -76,7 +76,7 @@ int main(int argc, char** argv) {
     if (argc > 6 && argv[6][0] == 'p') {   // feed S3 from the re-packed bank (TMA path), as vr_rerank_scores does
         void* packed;
         CK(cudaMalloc(&packed, vr::pair_fused_packed_bytes(n)));
-        if (vr::pair_fused_repack(d_bank, n, packed, 0)) return 1;
+        if (vr::pair_fused_repack(d_bank, n, 0, n, packed, 0)) return 1;
         a.c_packed_a = packed;
         a.q_packed_b = (const char*)packed + vr::pair_fused_packed_bytes(n) / 2;
         printf("re-packed bank (TMA-fed S3)\n");

@@ -40,11 +40,15 @@ struct vr_ctx {
     // arena: named device buffers that only grow
     std::unordered_map<std::string, std::pair<void*, size_t>> arena;
     cudaStream_t own_stream = nullptr;
-    cudaStream_t copy_stream = nullptr;   // uploads the patch bank while stage 0 runs (vr_evaluate_host)
-    cudaEvent_t patches_ready = nullptr;  // recorded on copy_stream; non-null pending_wait makes the next rerank wait for it
+    cudaStream_t copy_stream = nullptr;   // uploads the patch bank piece by piece while stage 0 runs (vr_evaluate_host)
+    cudaStream_t prep_stream = nullptr;   // re-packs every piece as it lands, under the upload of the next one
+    cudaEvent_t piece_ready[8] = {};      // recorded on copy_stream after each piece
+    cudaEvent_t patches_ready = nullptr;  // recorded on prep_stream; non-null pending_wait makes the next rerank wait for it
     bool pending_wait = false;
     float* dbg_err = nullptr;  // see vr_debug_err_trace
     bool packed_valid = false; // the fp16 re-pack of `patches` (arena "packed") matches the registered bank
+    int64_t packed_hi = 0;     // images [0, packed_hi) have been re-packed by vr_bank_prepare calls since the registration
+    int32_t* pinned = nullptr; // 16 pinned int32 for small device -> host reads (max num_pos)
 };
 
 using namespace vr;
@@ -105,13 +109,22 @@ int vr_create(int device, vr_ctx** out) {
         return rc;
     }
     ctx->max_clusters = mc;
+    if ((rc = pair_fused_ctx_open(device))) {
+        delete ctx;
+        return rc;
+    }
     rc = (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
           cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+          cudaStreamCreateWithFlags(&ctx->prep_stream, cudaStreamNonBlocking) == cudaSuccess &&
           cudaEventCreateWithFlags(&ctx->patches_ready, cudaEventDisableTiming) == cudaSuccess)
              ? VR_OK
              : VR_E_CUDA;
+    for (int i = 0; i < 8 && rc == VR_OK; i++)
+        if (cudaEventCreateWithFlags(&ctx->piece_ready[i], cudaEventDisableTiming) != cudaSuccess) rc = VR_E_CUDA;
+    if (rc == VR_OK && cudaHostAlloc((void**)&ctx->pinned, 64, cudaHostAllocDefault) != cudaSuccess) rc = VR_E_CUDA;
     if (rc) {
         set_error("vr_create: cudaStreamCreate failed");
+        pair_fused_ctx_close(device);
         delete ctx;
         return rc;
     }
@@ -126,8 +139,30 @@ int vr_destroy(vr_ctx* ctx) {
         if (kv.second.first) cudaFree(kv.second.first);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->prep_stream) cudaStreamDestroy(ctx->prep_stream);
+    for (int i = 0; i < 8; i++)
+        if (ctx->piece_ready[i]) cudaEventDestroy(ctx->piece_ready[i]);
     if (ctx->patches_ready) cudaEventDestroy(ctx->patches_ready);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    pair_fused_ctx_close(ctx->device);
     delete ctx;
+    return VR_OK;
+}
+
+int vr_num_pos(vr_ctx* ctx, const int64_t* labels, int64_t n, int32_t* num_pos, int32_t* max_num_pos_host, void* stream) {
+    VR_REQUIRE(ctx, "ctx is null");
+    VR_REQUIRE(labels && num_pos && n > 0, "num_pos: bad arguments");
+    VR_CHECK_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    void* d_max = nullptr;
+    int rc = arena_get(ctx, "np_max", 256, &d_max);
+    if (rc) return rc;
+    if ((rc = num_pos_counts(labels, n, num_pos, (int32_t*)d_max, st))) return rc;
+    if (max_num_pos_host) {
+        VR_CHECK_CUDA(cudaMemcpyAsync(ctx->pinned, d_max, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        VR_CHECK_CUDA(cudaStreamSynchronize(st));
+        *max_num_pos_host = ctx->pinned[0];
+    }
     return VR_OK;
 }
 
@@ -158,7 +193,28 @@ int vr_bank_register(vr_ctx* ctx, const float* patches, const float* centers, co
     ctx->n = n;
     ctx->c = c;
     ctx->r = r;
-    ctx->packed_valid = false;   // re-packed lazily by the first fused rerank on that call's stream
+    ctx->packed_valid = false;   // re-packed by vr_bank_prepare, or lazily by the first fused rerank on that call's stream
+    ctx->packed_hi = 0;
+    return VR_OK;
+}
+
+int vr_bank_prepare(vr_ctx* ctx, int64_t first, int64_t count, void* stream) {
+    VR_REQUIRE(ctx, "ctx is null");
+    if (!ctx->patches) {
+        set_error("bank_prepare: no bank registered");
+        return VR_E_NOBANK;
+    }
+    if (ctx->c != 128 || ctx->r != 49) return VR_OK;   // only the fused 7x7 / 128-channel kernel keeps an operand copy
+    VR_REQUIRE(first >= 0 && count > 0 && first + count <= ctx->n, "bank_prepare: range [%lld, %lld) outside the bank",
+               (long long)first, (long long)(first + count));
+    VR_REQUIRE(first <= ctx->packed_hi, "bank_prepare: ranges must be prepared in ascending order without gaps");
+    VR_CHECK_CUDA(cudaSetDevice(ctx->device));
+    void* packed = nullptr;
+    int rc = arena_get(ctx, "packed", pair_fused_packed_bytes(ctx->n), &packed);
+    if (rc) return rc;
+    if ((rc = pair_fused_repack(ctx->patches, ctx->n, first, count, packed, (cudaStream_t)stream))) return rc;
+    ctx->packed_hi = std::max(ctx->packed_hi, first + count);
+    if (ctx->packed_hi >= ctx->n) ctx->packed_valid = true;
     return VR_OK;
 }
 
@@ -233,7 +289,7 @@ int vr_rerank_scores(vr_ctx* ctx, int64_t q_start, int64_t q_stride, int64_t nq,
         void* packed = nullptr;
         if ((rc = arena_get(ctx, "packed", pair_fused_packed_bytes(ctx->n), &packed))) return rc;
         if (!ctx->packed_valid) {
-            if ((rc = pair_fused_repack(ctx->patches, ctx->n, packed, st))) return rc;
+            if ((rc = pair_fused_repack(ctx->patches, ctx->n, 0, ctx->n, packed, st))) return rc;
             ctx->packed_valid = true;
         }
         a.c_packed_a = packed;
@@ -292,8 +348,10 @@ int vr_sinkhorn(const float* K, const float* u, const float* v, int64_t b, int32
 }
 
 size_t vr_calc_similarity_workspace_bytes(int64_t n, int32_t c, int32_t r, const vr_ot_params* p) {
-    if (!p) return 0;
-    if (n <= 0x7fffffff && pair_fused_supports(c, r, (int)n, p)) return 256;
+    if (!p || n <= 0 || n >= 0x7fffffff) return 0;
+    (void)c;
+    // always the generic solver's size: the fused kernel needs none, but a misaligned view of a shape it supports is
+    // routed to the generic solver by vr_calc_similarity
     return generic_rerank_workspace_bytes(1, (int)n, r, p);
 }
 
@@ -458,33 +516,36 @@ int vr_evaluate_host(vr_ctx* ctx, const float* patches_host, const float* center
     if (rollout_host && (rc = arena_get(ctx, "h_rollout", br, &d_r))) return rc;
     if ((rc = arena_get(ctx, "h_labels", (size_t)n * 8, &d_l))) return rc;
     if ((rc = arena_get(ctx, "h_numpos", (size_t)n * 4, &d_np))) return rc;
-    // the big copy goes on its own stream: stage 0 needs the centres only and runs while the patches are in flight
-    VR_CHECK_CUDA(cudaMemcpyAsync(d_c, centers_host, bc, cudaMemcpyHostToDevice, st));
-    VR_CHECK_CUDA(cudaMemcpyAsync(d_p, patches_host, bp, cudaMemcpyHostToDevice, ctx->copy_stream));
-    VR_CHECK_CUDA(cudaEventRecord(ctx->patches_ready, ctx->copy_stream));
-    if (rollout_host) VR_CHECK_CUDA(cudaMemcpyAsync(d_r, rollout_host, br, cudaMemcpyHostToDevice, st));
+    // labels first: their class counts decide the shortlist length, and only the maximum comes back (4 bytes)
     VR_CHECK_CUDA(cudaMemcpyAsync(d_l, labels_host, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-    // num_pos[i] = #{j : label[j] == label[i]}  (metrics.py:34), computed while the copies fly
-    std::unordered_map<int64_t, int32_t> hist;
-    hist.reserve((size_t)n / 2 + 16);
-    for (int64_t i = 0; i < n; i++) hist[labels_host[i]]++;
-    std::vector<int32_t> np((size_t)n);
-    int32_t max_np = 1;
-    for (int64_t i = 0; i < n; i++) {
-        np[i] = hist[labels_host[i]];
-        max_np = std::max(max_np, np[i]);
-    }
-    VR_CHECK_CUDA(cudaMemcpyAsync(d_np, np.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
-    VR_CHECK_CUDA(cudaStreamSynchronize(st));  // np lives on this stack frame
+    VR_CHECK_CUDA(cudaMemcpyAsync(d_c, centers_host, bc, cudaMemcpyHostToDevice, st));
+    if (rollout_host) VR_CHECK_CUDA(cudaMemcpyAsync(d_r, rollout_host, br, cudaMemcpyHostToDevice, st));
     rc = vr_bank_register(ctx, (const float*)d_p, (const float*)d_c, (const float*)d_r, (const int64_t*)d_l,
                           (const int32_t*)d_np, n, c, r);
     if (rc) return rc;
+    // The patch bank goes up on its own stream in pieces: stage 0 needs the centres only and runs meanwhile, and every
+    // piece is re-packed into the operand layout of the fused kernel (vr_bank_prepare) while the next one is in flight.
+    const int pieces = (int)std::min<int64_t>(8, std::max<int64_t>(1, n / 512));
+    const int64_t per = (n + pieces - 1) / pieces;
+    for (int i = 0; i < pieces; i++) {
+        const int64_t lo = i * per, cnt = std::min(per, n - lo);
+        if (cnt <= 0) break;
+        VR_CHECK_CUDA(cudaMemcpyAsync((char*)d_p + (size_t)lo * c * r * 4, (const char*)patches_host + (size_t)lo * c * r * 4,
+                                      (size_t)cnt * c * r * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+        VR_CHECK_CUDA(cudaEventRecord(ctx->piece_ready[i], ctx->copy_stream));
+        VR_CHECK_CUDA(cudaStreamWaitEvent(ctx->prep_stream, ctx->piece_ready[i], 0));
+        if ((rc = vr_bank_prepare(ctx, lo, cnt, ctx->prep_stream))) return rc;
+    }
+    VR_CHECK_CUDA(cudaEventRecord(ctx->patches_ready, ctx->prep_stream));
+    // num_pos[i] = #{j : label[j] == label[i]} (metrics.py:34) on the device
+    int32_t max_np = 1;
+    if ((rc = vr_num_pos(ctx, (const int64_t*)d_l, n, (int32_t*)d_np, &max_np, st))) return rc;
     ctx->pending_wait = true;
     rc = vr_evaluate_registered(ctx, q_start, q_stride, nq, trunc_nums_host, n_trunc, max_np, p, tallies_host,
                                 per_query_niter_host, st);
     if (ctx->pending_wait) {   // no rerank ran (K = 0): still do not return before the upload has finished
         ctx->pending_wait = false;
-        VR_CHECK_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+        VR_CHECK_CUDA(cudaStreamSynchronize(ctx->prep_stream));
     }
     return rc;
 }

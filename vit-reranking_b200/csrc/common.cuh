@@ -173,6 +173,62 @@ __device__ __forceinline__ float torch_sum_inner(const float* x, int n) {
     return n >= 8 ? torch_sum_inner_w<8>(x, n) : torch_sum_inner_w<1>(x, n);
 }
 
+// The same order evaluated by a WARP: lane l < 8 carries vector lane l of ATen's 8-wide accumulators (the cascade's control
+// flow is the same for all lanes), the lanes are folded in order at the end.  Every lane of the warp must call; all return
+// the sum.  x may live in shared or global memory and must be visible to the whole warp.
+__device__ __forceinline__ float torch_sum_inner_warp(const float* x, int n, int lane) {
+    if (n < 8) {   // ATen's scalar path (ILP 4, no vector lanes)
+        float s = 0.f;
+        if (lane == 0) s = torch_sum_inner_w<1>(x, n);
+        return __shfl_sync(0xffffffffu, s, 0);
+    }
+    constexpr int W = 8, ILP = 4, LEVELS = 4;
+    const int l = lane & 7;
+    const int vec_size = n / W;
+    const int size_ilp = vec_size / ILP;
+    float acc[LEVELS][ILP];
+#pragma unroll
+    for (int a = 0; a < LEVELS; a++)
+#pragma unroll
+        for (int k = 0; k < ILP; k++) acc[a][k] = 0.f;
+    int lg = 0;
+    while ((1 << lg) < size_ilp) lg++;
+    const int level_power = max(4, lg / LEVELS);
+    const int level_step = 1 << level_power;
+    const int level_mask = level_step - 1;
+    int i = 0;
+    for (; i + level_step <= size_ilp;) {
+        for (int j = 0; j < level_step; ++j, ++i)
+#pragma unroll
+            for (int k = 0; k < ILP; k++) acc[0][k] += x[(i * ILP + k) * W + l];
+#pragma unroll
+        for (int j = 1; j < LEVELS; ++j) {
+#pragma unroll
+            for (int k = 0; k < ILP; k++) {
+                acc[j][k] += acc[j - 1][k];
+                acc[j - 1][k] = 0.f;
+            }
+            const int mask = level_mask << (j * level_power);
+            if ((i & mask) != 0) break;
+        }
+    }
+    for (; i < size_ilp; ++i)
+#pragma unroll
+        for (int k = 0; k < ILP; k++) acc[0][k] += x[(i * ILP + k) * W + l];
+#pragma unroll
+    for (int j = 1; j < LEVELS; ++j)
+#pragma unroll
+        for (int k = 0; k < ILP; k++) acc[0][k] += acc[j][k];
+    for (i = size_ilp * ILP; i < vec_size; ++i) acc[0][0] += x[i * W + l];
+#pragma unroll
+    for (int k = 1; k < ILP; k++) acc[0][0] += acc[0][k];
+    float fin = 0.f;
+    for (int k = vec_size * W; k < n; ++k) fin += x[k];
+#pragma unroll
+    for (int w = 0; w < W; w++) fin += __shfl_sync(0xffffffffu, acc[0][0], w);
+    return fin;
+}
+
 // ---- mbarrier + bulk async copy (TMA 1-D) --------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);

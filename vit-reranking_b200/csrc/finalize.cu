@@ -6,6 +6,8 @@
 // counts the query itself).  Recall@1/2/4/8 is an extension named by BASELINE.json.
 // Only final_tops[:num_pos] is ever read by the reference, so the first-stage shortlist of
 // length kp >= max(k, num_pos) carries everything needed; nothing N-long is materialised.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -34,6 +36,9 @@ __global__ void __launch_bounds__(FN_WARPS * 32) finalize_kernel(FinalizeArgs a)
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw) + (size_t)warp * k;
     int32_t* rer = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned long long*>(smem_raw) + (size_t)FN_WARPS * k) +
                    (size_t)warp * k;
+    // precision@j terms of MAP@R, fp32 like the reference's tensor (metrics.py:43-45)
+    float* terms = reinterpret_cast<float*>(reinterpret_cast<int32_t*>(reinterpret_cast<unsigned long long*>(smem_raw) + (size_t)FN_WARPS * k) +
+                                            (size_t)FN_WARPS * k) + (size_t)warp * kp;
     const int64_t qi = (int64_t)blockIdx.x * FN_WARPS + warp;
     if (qi >= a.nq) return;
     const int64_t qid = a.q_start + qi * a.q_stride;
@@ -67,7 +72,6 @@ __global__ void __launch_bounds__(FN_WARPS * 32) finalize_kernel(FinalizeArgs a)
         const int t = a.truncs[ti];
         const int tt = min(t, keff);  // entries taken from the reranked list
         int cum = 0;                  // hits before the current 32-wide window
-        double ap = 0.0;
         unsigned first8 = 0;
         const int lim = max(upto, min(8, nvalid));  // Recall@8 looks at 8 entries even if num_pos < 8
         for (int base = 0; base < lim; base += 32) {
@@ -85,18 +89,21 @@ __global__ void __launch_bounds__(FN_WARPS * 32) finalize_kernel(FinalizeArgs a)
             if (base == 0) first8 = __ballot_sync(0xffffffffu, hit) & 0xffu;
             hit = hit && j < upto;
             const unsigned m = __ballot_sync(0xffffffffu, hit);
-            if (hit) {
+            if (j < upto) {   // (cum * eq) / k_idx: fp32 / int64 -> fp32 division (metrics.py:43-45)
                 const int c = cum + __popc(m & (0xffffffffu >> (31 - lane)));
-                ap += (double)((float)c / (float)(j + 1));
+                terms[j] = hit ? (float)c / (float)(j + 1) : 0.f;
             }
             cum += __popc(m);
         }
-        for (int o = 16; o > 0; o >>= 1) ap += __shfl_xor_sync(0xffffffffu, ap, o);
+        __syncwarp();
+        // torch.mean over the num_pos terms = ATen's fp32 sum (cascade order, common.cuh) followed by one fp32 division
+        const float ap = torch_sum_inner_warp(terms, upto, lane);
+        __syncwarp();
         if (lane == 0) {
             double* out = a.per_query + (qi * a.n_trunc + ti) * FN_METRICS;
             out[0] = (first8 & 1u) ? 1.0 : 0.0;
             out[1] = (double)((float)cum / (float)np);
-            out[2] = (double)(float)(ap / (double)np);
+            out[2] = (double)(ap / (float)upto);
             out[3] = (first8 & 0x1u) ? 1.0 : 0.0;
             out[4] = (first8 & 0x3u) ? 1.0 : 0.0;
             out[5] = (first8 & 0xfu) ? 1.0 : 0.0;
@@ -123,9 +130,10 @@ __global__ void __launch_bounds__(256) tally_kernel(const double* per_query, int
 
 
 // Direct call: evaluation/metrics.py:26-47 for ONE ranked list (tops may be N long; only
-// tops[:num_pos] is read).  out = {r1, rp, mapr}.
+// tops[:num_pos] is read).  out = {r1, rp, mapr}.  `terms` is scratch for min(n_tops, n_labels) floats.
 __global__ void __launch_bounds__(256) metrics_rank_kernel(const int64_t* tops, int64_t n_tops, int64_t qlabel,
-                                                           const int64_t* labels, int64_t n_labels, double* out) {
+                                                           const int64_t* labels, int64_t n_labels, float* terms,
+                                                           double* out) {
     __shared__ int red[8];
     __shared__ int s_np;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -144,7 +152,6 @@ __global__ void __launch_bounds__(256) metrics_rank_kernel(const int64_t* tops, 
     const int np = s_np;
     const int64_t upto = min((int64_t)np, n_tops);
     int cum = 0;
-    double ap = 0.0;
     bool first = false;
     for (int64_t base = 0; base < upto; base += 32) {
         const int64_t j = base + lane;
@@ -155,24 +162,63 @@ __global__ void __launch_bounds__(256) metrics_rank_kernel(const int64_t* tops, 
         }
         const unsigned m = __ballot_sync(0xffffffffu, hit);
         if (base == 0) first = (m & 1u) != 0;
-        if (hit) {
+        if (j < upto) {
             const int c = cum + __popc(m & (0xffffffffu >> (31 - lane)));
-            ap += (double)((float)c / (float)(j + 1));
+            terms[j] = hit ? (float)c / (float)(j + 1) : 0.f;   // fp32, like (cum * eq) / k_idx (metrics.py:43-45)
         }
         cum += __popc(m);
     }
-    for (int o = 16; o > 0; o >>= 1) ap += __shfl_xor_sync(0xffffffffu, ap, o);
+    __syncwarp();
+    // torch.mean = ATen's fp32 cascade sum, then one fp32 division
+    const float ap = upto > 0 ? torch_sum_inner_warp(terms, (int)upto, lane) : 0.f;
     if (lane == 0) {
         out[0] = first ? 1.0 : 0.0;
         out[1] = np > 0 ? (double)((float)cum / (float)np) : 0.0;
-        out[2] = np > 0 ? (double)(float)(ap / (double)np) : 0.0;
+        out[2] = upto > 0 ? (double)(ap / (float)upto) : 0.0;
     }
 }
 
 int metrics_rank(const int64_t* tops, int64_t n_tops, int64_t qlabel, const int64_t* labels, int64_t n_labels,
                  double* out, cudaStream_t st) {
     VR_REQUIRE(tops && labels && out && n_tops > 0 && n_labels > 0, "metrics_rank: bad arguments");
-    metrics_rank_kernel<<<1, 256, 0, st>>>(tops, n_tops, qlabel, labels, n_labels, out);
+    VR_REQUIRE(n_labels < 0x7fffffffll, "metrics_rank: gallery too large");
+    float* terms = nullptr;   // stream-ordered scratch: num_pos is only known on the device
+    VR_CHECK_CUDA(cudaMallocAsync(&terms, (size_t)std::min(n_tops, n_labels) * sizeof(float), st));
+    metrics_rank_kernel<<<1, 256, 0, st>>>(tops, n_tops, qlabel, labels, n_labels, terms, out);
+    VR_LAUNCH_CHECK();
+    VR_CHECK_CUDA(cudaFreeAsync(terms, st));
+    return VR_OK;
+}
+
+// num_pos[i] = #{j : labels[j] == labels[i]} (metrics.py:34, counts the query itself) and the largest such count,
+// by brute force over label tiles in shared memory: n^2 64-bit compares (3.7e9 at SOP size: ~0.2 ms), no sort, no hash
+// table, no host pass over the labels.
+constexpr int NP_THREADS = 256;
+constexpr int NP_TILE = 2048;
+__global__ void __launch_bounds__(NP_THREADS) num_pos_kernel(const int64_t* __restrict__ labels, int64_t n, int32_t* __restrict__ num_pos,
+                                                             int32_t* __restrict__ max_out) {
+    __shared__ int64_t tile[NP_TILE];
+    const int64_t i = (int64_t)blockIdx.x * NP_THREADS + threadIdx.x;
+    const int64_t mine = i < n ? labels[i] : 0;
+    int cnt = 0;
+    for (int64_t base = 0; base < n; base += NP_TILE) {
+        const int m = (int)min((int64_t)NP_TILE, n - base);
+        __syncthreads();
+        for (int t = threadIdx.x; t < m; t += NP_THREADS) tile[t] = labels[base + t];
+        __syncthreads();
+#pragma unroll 8
+        for (int t = 0; t < m; t++) cnt += (tile[t] == mine) ? 1 : 0;
+    }
+    if (i < n) num_pos[i] = cnt;
+    cnt = i < n ? cnt : 0;
+    cnt = __reduce_max_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0) atomicMax(max_out, cnt);
+}
+
+int num_pos_counts(const int64_t* labels, int64_t n, int32_t* num_pos, int32_t* max_dev, cudaStream_t st) {
+    VR_REQUIRE(labels && num_pos && max_dev && n > 0 && n < 0x7fffffffll, "num_pos: bad arguments");
+    VR_CHECK_CUDA(cudaMemsetAsync(max_dev, 0, sizeof(int32_t), st));
+    num_pos_kernel<<<(unsigned)((n + NP_THREADS - 1) / NP_THREADS), NP_THREADS, 0, st>>>(labels, n, num_pos, max_dev);
     VR_LAUNCH_CHECK();
     return VR_OK;
 }
@@ -211,7 +257,7 @@ int finalize(int64_t q_start, int64_t q_stride, int64_t nq, int k, int kp, const
     }
     a.out_rank = out_rank;
     a.per_query = reinterpret_cast<double*>(ws);
-    size_t smem = (size_t)FN_WARPS * k * (8 + 4) + 16;
+    size_t smem = (size_t)FN_WARPS * k * (8 + 4) + (size_t)FN_WARPS * kp * 4 + 16;
     VR_REQUIRE(smem <= 200 * 1024, "finalize: k=%d too large", k);
     if (smem > 48 * 1024)
         VR_CHECK_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

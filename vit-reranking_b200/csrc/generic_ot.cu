@@ -341,7 +341,12 @@ __global__ void __launch_bounds__(256) generic_decide_kernel(IterArgs a, int it,
     const int64_t qi = blockIdx.x;
     if (a.done[qi]) return;
     float s = 0.f;
-    for (int i = threadIdx.x; i < a.k; i += 256) s += fmaxf(a.e[qi * a.k + i], 0.f);
+    // padded shortlist entries carry e = -1 and add nothing; NaN / inf propagate into the mean, so that `mean < thresh`
+    // is false and the query runs all its iterations like the reference's `nan < thresh` (diml.py:50-52)
+    for (int i = threadIdx.x; i < a.k; i += 256) {
+        const float e = a.e[qi * a.k + i];
+        s += (e < 0.f) ? 0.f : e;
+    }
     s = block_reduce_sum(s, red);
     if (threadIdx.x == 0) {
         a.niter[qi] = it + 1;

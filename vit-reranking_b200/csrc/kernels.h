@@ -68,8 +68,10 @@ int pair_fused_max_clusters(int* out);
 bool pair_fused_supports(int c, int r, int k, const vr_ot_params* p);
 bool pair_fused_supports_wide(int c, int r, int k, const vr_ot_params* p);   // 112 < k <= 1024, scores only
 int pair_fused_launch(const PairArgs& a, int64_t nq, cudaStream_t st);
+int pair_fused_ctx_open(int device);    // vr_create / vr_destroy: the last context on a device frees the exchange buffer
+void pair_fused_ctx_close(int device);
 size_t pair_fused_packed_bytes(int64_t n);   // both roles
-int pair_fused_repack(const float* patches, int64_t n, void* packed, cudaStream_t st);
+int pair_fused_repack(const float* patches, int64_t n, int64_t first, int64_t count, void* packed, cudaStream_t st);
 
 // generic_ot.cu
 size_t generic_rerank_workspace_bytes(int64_t nq, int k, int r, const vr_ot_params* p);
@@ -84,6 +86,8 @@ int finalize(int64_t q_start, int64_t q_stride, int64_t nq, int k, int kp, const
              const float* approx_score, const float* ot_score, const int64_t* labels, const int32_t* num_pos,
              const int32_t* truncs, int n_trunc, int32_t* out_rank, double* tallies, void* ws, size_t ws_bytes,
              cudaStream_t st);
+
+int num_pos_counts(const int64_t* labels, int64_t n, int32_t* num_pos, int32_t* max_dev, cudaStream_t st);
 
 int metrics_rank(const int64_t* tops, int64_t n_tops, int64_t qlabel, const int64_t* labels, int64_t n_labels,
                  double* out, cudaStream_t st);

@@ -17,6 +17,8 @@ What changed underneath (reference file:line in brackets):
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -169,12 +171,27 @@ def evaluate_banks(patches, centers, rollout, labels, trunc_nums=None, use_unifo
 
 def evaluate(model, dataset, dataloader, training=False, trunc_nums=None, use_uniform=False, grid_size=4,
              use_inverse=False, temperature=1.0, use_cls_token=False, attn_blk_ind=0, use_ot=True, ot_part=0.1,
-             to_submit=False, use_minus=False, use_rollout=False, plot_topk=1, visual_hook=None):
-    """evaluation/eval_cvt_diml.py:196-416."""
+             to_submit=False, use_minus=False, use_rollout=False, plot_topk=1, visual_hook=None, bank_cache=None):
+    """evaluation/eval_cvt_diml.py:196-416.  bank_cache (or $VITRERANK_BANK_CACHE): path of an on-disk bank
+    (vitrerank/bankfile.py) -- read instead of embedding when it exists and has the rollout bank the flags need,
+    written after embedding otherwise; the working form of the cache the reference keeps disabled
+    (evaluation/eval_diml.py:80-85,151-153)."""
     device = torch.device('cuda')
     model.eval()
-    patches, centers, rollout, labels = embed_banks(model, dataloader, training=training, grid_size=grid_size,
-                                                    use_rollout=use_rollout, device=device)
+    bank_cache = bank_cache or os.environ.get("VITRERANK_BANK_CACHE")
+    banks = None
+    if bank_cache and os.path.exists(bank_cache):
+        from vitrerank import bankfile
+        banks = bankfile.load(bank_cache)
+        if banks[3] is None or (use_rollout and not use_uniform and banks[2] is None):
+            banks = None    # written by a run without labels / rollout: embed again
+    if banks is None:
+        banks = embed_banks(model, dataloader, training=training, grid_size=grid_size, use_rollout=use_rollout,
+                            device=device)
+        if bank_cache:
+            from vitrerank import bankfile
+            bankfile.save(bank_cache, *banks)
+    patches, centers, rollout, labels = banks
     trunc_nums = trunc_nums or [0, 5, 10, 50, 100, 500, 1000]
     data = evaluate_banks(patches, centers, rollout, labels, trunc_nums=trunc_nums, use_uniform=use_uniform,
                           use_inverse=use_inverse, temperature=temperature, use_cls_token=use_cls_token,

@@ -40,6 +40,8 @@ def _load():
         "vr_destroy": (C.c_int, [vp]),
         "vr_device_info": (C.c_int, [vp, P(i32), P(i32)]),
         "vr_bank_register": (C.c_int, [vp, vp, vp, vp, vp, vp, i64, i32, i32]),
+        "vr_bank_prepare": (C.c_int, [vp, i64, i64, vp]),
+        "vr_num_pos": (C.c_int, [vp, vp, i64, vp, P(i32), vp]),
         "vr_stage0_workspace_bytes": (sz, [vp, i64, i32]),
         "vr_stage0_topk": (C.c_int, [vp, vp, vp, i64, i64, i64, i32, vp, vp, vp, sz, vp]),
         "vr_rerank_workspace_bytes": (sz, [vp, i64, i32, P(OTParamsStruct)]),

@@ -7,9 +7,10 @@ the [len(trunc_nums), 8] fp64 tallies (NCCL over NVLink on GPUs; gloo in the CPU
 
 When the banks start on the HOST (the reference keeps the patch bank in CPU memory,
 eval_cvt_diml.py:278), replicating the gallery would push the same 204 MB through every GPU's PCIe
-link.  `evaluate_host_sharded` sends every image over PCIe once per node instead — rank r uploads
-images [r*m, (r+1)*m) — and the ranks all-gather the rest over NVLink (one NCCL all-gather, in
-place), while stage 0, which needs only the centres, already runs.
+link.  `evaluate_host_sharded` sends every image over PCIe once per node instead — the gallery is cut
+into pieces of W slices, rank r uploads slice r of every piece — and the ranks all-gather each piece
+over NVLink (NCCL, in place) as soon as it has landed, while the next piece is still on PCIe and
+while stage 0, which needs only the centres, already runs.
 """
 from __future__ import annotations
 
@@ -63,45 +64,71 @@ def evaluate_sharded(engine, trunc_nums, params, gather_niter=False):
     return tallies, niter
 
 
+HOST_PIECES = 4   # upload / all-gather pipeline depth of evaluate_host_sharded
+
+
 def evaluate_host_sharded(engine, patches, centers, rollout, labels, trunc_nums, params):
     """Host banks (CPU tensors, pinned for full PCIe speed) -> all-reduced tallies [len(trunc_nums), 8].
     Returns (tallies, h2d_bytes_of_this_rank).  Without an NCCL group of more than one rank this is
-    engine.evaluate_host on the rank's query shard plus the tally all-reduce."""
+    engine.evaluate_host (the C-ABI host entry) on the rank's query shard plus the tally all-reduce.
+
+    With W ranks every image crosses PCIe once per node: the gallery is cut into HOST_PIECES pieces of W slices; rank r
+    uploads slice r of every piece on a copy stream, each piece is all-gathered in place over NVLink as soon as its
+    slices have landed (while the next piece is still in flight on PCIe) and re-packed into the operand layout of the
+    fused kernel (vr_bank_prepare) on the same side stream.  Stage 0 needs only the centres and runs meanwhile on the
+    main stream; the rerank waits for the last piece."""
     import torch.distributed as dist
     rank, w = world()
     n, c, r = patches.shape
     q_start, q_stride, nq = shard(n, rank, w)
     k = max(int(t) for t in trunc_nums)
     small = centers.numel() * 4 + (0 if rollout is None else rollout.numel() * 4) + labels.numel() * 8
-    if w == 1 or dist.get_backend() != "nccl" or k == 0 or n < 2 * w:
+    if w == 1 or dist.get_backend() != "nccl" or k == 0 or n < 2 * w * HOST_PIECES:
         tallies = engine.evaluate_host(patches, centers, rollout, labels, trunc_nums, params, q_start=q_start,
                                        q_stride=q_stride, nq=nq)
         return all_reduce_tallies(tallies, engine.device), patches.numel() * 4 + small
     dev = engine.device
-    m = (n + w - 1) // w                       # images uploaded per rank
-    lo, hi = rank * m, min(n, (rank + 1) * m)
+    pieces = HOST_PIECES
+    mp = (n + w * pieces - 1) // (w * pieces)       # images per (piece, rank) slice
+    total = w * pieces * mp                          # >= n; the tail is never referenced
     st = getattr(engine, "_host_shard_state", None)
-    if st is None or st["shape"] != (w * m, c, r):
-        st = dict(shape=(w * m, c, r), buf=torch.empty(w * m, c, r, dtype=torch.float32, device=dev),
-                  stream=torch.cuda.Stream(dev), event=torch.cuda.Event())
+    if st is None or st["shape"] != (total, c, r):
+        st = dict(shape=(total, c, r), buf=torch.empty(total, c, r, dtype=torch.float32, device=dev),
+                  copy=torch.cuda.Stream(dev), side=torch.cuda.Stream(dev),
+                  landed=[torch.cuda.Event() for _ in range(pieces)], ready=torch.cuda.Event())
         engine._host_shard_state = st
-    buf, copy_stream, ev = st["buf"], st["stream"], st["event"]
+    buf, copy_stream, side = st["buf"], st["copy"], st["side"]
     cur = torch.cuda.current_stream(dev)
     copy_stream.wait_stream(cur)               # the previous pass is done with the buffer
-    with torch.cuda.stream(copy_stream):
-        if hi > lo:
-            buf[lo:hi].copy_(patches[lo:hi], non_blocking=True)
-        ev.record(copy_stream)
+    side.wait_stream(cur)
+    labels_d = labels.to(dev, non_blocking=True)
     centers_d = centers.to(dev, non_blocking=True)
     rollout_d = None if rollout is None else rollout.to(dev, non_blocking=True)
-    labels_d = labels.to(dev, non_blocking=True)
+    h2d = small
+    with torch.cuda.stream(copy_stream):
+        for p in range(pieces):
+            lo = (p * w + rank) * mp
+            hi = min(n, lo + mp)
+            if hi > lo:
+                buf[lo:hi].copy_(patches[lo:hi], non_blocking=True)
+                h2d += (hi - lo) * c * r * 4
+            st["landed"][p].record(copy_stream)
     engine.register(buf[:n], centers_d, rollout_d, labels_d)     # pointers only; the patches are still in flight
+    with torch.cuda.stream(side):
+        for p in range(pieces):
+            side.wait_event(st["landed"][p])
+            piece = buf[p * w * mp:(p + 1) * w * mp]
+            dist.all_gather_into_tensor(piece.view(-1), piece[rank * mp:(rank + 1) * mp].view(-1))   # in place, NVLink
+            lo = p * w * mp
+            hi = min(n, lo + w * mp)
+            if hi > lo:
+                engine.prepare_bank(lo, hi - lo, stream=side)
+        st["ready"].record(side)
     kp = max(k, engine.bank["max_num_pos"], 8)
     idx, approx = engine.stage0_topk(kp, q_start=q_start, q_stride=q_stride, nq=nq)
-    cur.wait_event(ev)
-    dist.all_gather_into_tensor(buf.view(-1), buf[lo:lo + m].view(-1))   # in place, NVLink
+    cur.wait_event(st["ready"])
     score, _ = engine.rerank_scores(idx, k, params, q_start=q_start, q_stride=q_stride)
     t_dev = torch.zeros(len(trunc_nums), 8, dtype=torch.float64, device=dev)
     engine.finalize(idx, approx, score, k, trunc_nums, q_start=q_start, q_stride=q_stride, tallies=t_dev)
     dist.all_reduce(t_dev)
-    return t_dev.cpu().numpy(), (hi - lo) * c * r * 4 + small
+    return t_dev.cpu().numpy(), h2d

@@ -133,24 +133,45 @@ class RerankEngine:
         return self._trace
 
     # ---- gallery -----------------------------------------------------------------------
-    def register(self, patches, centers, rollout=None, labels=None):
+    def num_pos(self, labels):
+        """(num_pos [N] int32 on the device, its maximum): num_pos[i] = #{j: labels[j] == labels[i]}, the
+        `torch.sum(gallery_label == query_label)` of metrics.py:34 for every item (counts the item itself)."""
+        labels = labels.to(device=self.device, dtype=torch.int64).contiguous()
+        out = torch.empty(labels.numel(), dtype=torch.int32, device=self.device)
+        mx = C.c_int32(0)
+        check(lib.vr_num_pos(self._h, _ptr(labels), labels.numel(), _ptr(out), C.byref(mx), _stream(self.device)),
+              "vr_num_pos")
+        return out, int(mx.value)
+
+    def register(self, patches, centers, rollout=None, labels=None, num_pos=None, max_num_pos=None):
         """patches [N,C,R], centers [N,C], rollout [N,R], labels [N]; moved to the device if
-        needed (the reference keeps the patch bank on the host, eval_cvt_diml.py:278)."""
+        needed (the reference keeps the patch bank on the host, eval_cvt_diml.py:278).  num_pos / max_num_pos
+        (from a previous num_pos() call on the same labels) skip the label count."""
         dev = self.device
         patches, centers, rollout = _f32(patches, dev), _f32(centers, dev), _f32(rollout, dev)
         n, c, r = patches.shape
-        num_pos = None
         max_np = 1
         if labels is not None:
             labels = labels.to(device=dev, dtype=torch.int64).contiguous()
-            _, inv, cnt = torch.unique(labels, return_inverse=True, return_counts=True)
-            num_pos = cnt[inv].to(torch.int32).contiguous()   # metrics.py:34 (counts the query itself)
-            max_np = int(cnt.max().item())
+            if num_pos is None or max_num_pos is None:
+                num_pos, max_np = self.num_pos(labels)
+            else:
+                num_pos, max_np = num_pos.to(device=dev, dtype=torch.int32).contiguous(), int(max_num_pos)
+        else:
+            num_pos = None
         check(lib.vr_bank_register(self._h, _ptr(patches), _ptr(centers), _ptr(rollout), _ptr(labels),
                                    _ptr(num_pos), n, c, r), "vr_bank_register")
         self._bank = dict(patches=patches, centers=centers, rollout=rollout, labels=labels, num_pos=num_pos,
                           n=n, c=c, r=r, max_num_pos=max_np)
         return self
+
+    def prepare_bank(self, first=0, count=None, stream=None):
+        """Derive the library's operand copy of images [first, first + count) now (vr_bank_prepare), on `stream`
+        (a torch.cuda.Stream; default: the current one).  Optional: the first fused rerank does it otherwise."""
+        b = self.bank
+        count = b["n"] - first if count is None else count
+        sp = C.c_void_p(stream.cuda_stream) if stream is not None else _stream(self.device)
+        check(lib.vr_bank_prepare(self._h, first, count, sp), "vr_bank_prepare")
 
     @property
     def bank(self):
@@ -199,7 +220,9 @@ class RerankEngine:
 
     # ---- S5b ---------------------------------------------------------------------------------
     def finalize(self, approx_idx, approx_score, ot_score, k, trunc_nums, q_start=0, q_stride=1, tallies=None,
-                 want_rank=False):
+                 want_rank=False, want_per_query=False):
+        """Returns (tallies, rank) or, with want_per_query, (tallies, rank, per_query [nq, len(trunc_nums), 8] float64:
+        the r1 / rp / mapr / recall@1,2,4,8 / 1 of every query, columns METRIC_COLS)."""
         nq, kp = approx_idx.shape
         nt = len(trunc_nums)
         if tallies is None:
@@ -211,6 +234,9 @@ class RerankEngine:
         check(lib.vr_finalize(self._h, q_start, q_stride, nq, k, kp, _ptr(approx_idx), _ptr(approx_score),
                               _ptr(ot_score), tr, nt, _ptr(rank), _ptr(tallies), _ptr(ws), ws.numel(),
                               _stream(self.device)), "vr_finalize")
+        if want_per_query:   # the head of the workspace is the per-query table the tallies were summed from
+            pq = ws[:nq * nt * 8 * 8].view(torch.float64).view(nq, nt, 8).clone()
+            return tallies, rank, pq
         return tallies, rank
 
     # ---- whole pass over the registered (device-resident) gallery ---------------------------------
