@@ -279,3 +279,33 @@ def test_reference_caller_runs_unchanged_under_shims(tmp_path):
     assert call["grid_size"] == 7 and abs(call["temperature"] - 0.1) < 1e-12 and call["ot_part"] == 1.0
     csv = (tmp_path / "test_results" / "test_diml_cub200.csv").read_text()  # :158-161
     assert "method,r1,rp,mapr" in csv.replace(" ", "") and "ours (100)" in csv
+
+
+def test_bank_file_roundtrip_and_rejects_damage(tmp_path):
+    """vitrerank/bankfile.py: the on-disk bank (the cache the reference keeps disabled, evaluation/eval_diml.py:80-85,
+    151-153) round-trips bit for bit, mmap or not, with and without the optional banks, and refuses damaged files."""
+    from vitrerank import bankfile as B, synth
+    g = synth.make_gallery(37, 16, 9, classes=3, seed=2)
+    p = str(tmp_path / "a.vrbank")
+    nbytes = B.save(p, g.patches, g.centers, g.rollout, g.labels)
+    assert os.path.getsize(p) == nbytes
+    for mm in (True, False):
+        pt, ce, ro, la = B.load(p, mmap=mm)
+        assert torch.equal(pt, g.patches) and torch.equal(ce, g.centers) and torch.equal(ro, g.rollout)
+        assert torch.equal(la, g.labels)
+    B.save(p, g.patches, g.centers)
+    pt, ce, ro, la = B.load(p)
+    assert ro is None and la is None and torch.equal(pt, g.patches)
+    raw = bytearray(open(p, "rb").read())
+    bad = str(tmp_path / "b.vrbank")
+    for pos, what in ((3, "not a vitrerank bank"), (7, "version"), (200, "checksum")):
+        dmg = bytearray(raw)
+        dmg[pos] ^= 0x20
+        open(bad, "wb").write(dmg)
+        with pytest.raises(B.BankFileError, match=what):
+            B.load(bad)
+    open(bad, "wb").write(raw[:-64])
+    with pytest.raises(B.BankFileError, match="header says"):
+        B.load(bad)
+    with pytest.raises(B.BankFileError):
+        B.save(bad, g.patches, g.centers[:5])

@@ -185,3 +185,56 @@ def test_torch_sum_order(n):
     ref = torch.from_numpy(x).sum(dim=1, keepdim=True).numpy()[:, 0]
     got = _torch_sum_order(x)
     assert np.array_equal(got.view(np.int32), ref.view(np.int32))
+
+
+# ---- the restatement against the REAL reference functions, live (checkout here, oracle/_ref on the GPU box) ----
+@pytest.mark.parametrize("flags", [dict(use_rollout=True, ot_part=1.0),
+                                   dict(use_inverse=True, temperature=0.1, use_cls_token=True, ot_part=1.0),
+                                   dict(use_minus=True, ot_part=0.5)])
+def test_oracle_equals_real_reference_loop(flags):
+    from oracle import ref_loader as RL
+    if RL.root() is None:
+        pytest.skip("neither /root/reference nor oracle/_ref present (python oracle/make_ref.py)")
+    g = synth.make_gallery(150, 128, 49, classes=5, seed=17, sigma=0.6)
+    ids = list(range(0, 150, 6))
+    kw = dict(flags)
+    use_rollout = kw.pop("use_rollout", False)
+    ref = RL.reference_loop(g.patches, g.centers, g.rollout, g.labels, [0, 20, 100], use_rollout=use_rollout,
+                            query_ids=ids, **kw)
+    out = O.evaluate_banks(g.patches, g.centers, g.rollout, g.labels, trunc_nums=[0, 20, 100], query_ids=ids, dump=True,
+                           **flags)
+    for a, b in zip(ref["per_query"], out["dump"]):
+        assert torch.equal(a["score"], b["score"])            # bit-identical per-pair scores
+        assert a["metrics"] == b["metrics"]                   # and per-query r1 / rp / mapr
+    for key in ("r1", "rp", "mapr"):
+        assert ref[key] == out[key]
+
+
+def test_parallel_runner_and_parity_counters():
+    from oracle import parallel as OP
+    from oracle import parity as PAR
+    g = synth.make_gallery(120, 128, 49, classes=4, seed=23, sigma=0.6)
+    ids = list(range(1, 120, 5))
+    flags = dict(use_rollout=True, ot_part=1.0)
+    serial = O.evaluate_banks(g.patches, g.centers, g.rollout, g.labels, trunc_nums=[0, 50], query_ids=ids, dump=True,
+                              **flags)["dump"]
+    par, _, procs = OP.run(g, ids, [0, 50], flags, procs=3, chunk=4)
+    assert len(par) == len(ids) and [d["q"] for d in par] == ids
+    for a, b in zip(serial, par):
+        assert torch.equal(a["score"], b["score"]) and a["n_iter"] == b["n_iter"] and a["metrics"] == b["metrics"]
+    # the oracle against itself: nothing to count
+    idx = np.stack([d["top"].numpy() for d in par])
+    score = np.stack([d["score"].numpy() for d in par])
+    nit = np.array([d["n_iter"] for d in par])
+    pq = np.array([[list(d["metrics"][t]) for t in (0, 50)] for d in par])
+    c = PAR.compare(par, idx, score, nit, 50, trunc_nums=[0, 50], per_query=pq)
+    assert c["niter_equal"] == len(ids) and c["pairs_over_1e-4"] == 0 and c["metric_mismatch_queries"] == 0
+    assert c["stage0_set_mismatch"] == 0 and c["max_rel_err"] == 0.0 and c["pairs"] == 50 * len(ids)
+    # and a doctored copy: one iteration count off, one score beyond the gate, one shortlist member swapped
+    nit2, score2, idx2 = nit.copy(), score.copy(), idx.copy()
+    nit2[0] += 1
+    score2[1, 3] *= 1.001
+    idx2[2, 0] = [i for i in range(120) if i not in set(idx[2].tolist())][0]
+    c = PAR.compare(par, idx2, score2, nit2, 50, trunc_nums=[0, 50], per_query=pq)
+    assert c["niter_off_by_one"] == 1 and c["pairs_over_1e-4"] == 1 and c["stage0_set_mismatch"] == 1
+    assert c["pairs_over_1e-4_in_equal_niter_queries"] == 1 and c["queries_with_pairs_over_1e-4"] == 1
