@@ -38,6 +38,8 @@ def compare(dumps, idx, score, niter, k, trunc_nums=None, per_query=None, thresh
          "flips_outside_2pct_band": 0, "max_flip_err_distance": 0.0, "pairs_over_1e-4": 0,
          "pairs_over_1e-4_in_equal_niter_queries": 0, "max_rel_err": 0.0, "max_rel_err_equal_niter": 0.0,
          "queries_with_pairs_over_1e-4": 0, "metric_mismatch_queries": 0, "metric_mismatch_queries_equal_niter": 0,
+         "stage0_order_differs_within_tie": 0, "stage0_order_differs_beyond_tie": 0,
+         "metric_mismatch_unexplained": 0,
          "mean_niter_cuda": float(niter[:nq].mean()) if nq else 0.0,
          "mean_niter_oracle": float(np.mean([d["n_iter"] for d in dumps])) if nq else 0.0}
     dt = {t: [0.0, 0.0, 0.0] for t in (trunc_nums or [])}
@@ -52,6 +54,17 @@ def compare(dumps, idx, score, niter, k, trunc_nums=None, per_query=None, thresh
             c["stage0_set_mismatch"] += 1
             if not d.get("gap", 1.0) < TIE:
                 c["stage0_set_mismatch_beyond_tie"] += 1
+        # order inside the shortlist: torch's matvec and the CUDA FMA chain round the global scores differently, so two
+        # candidates whose scores agree to 1e-6 may swap places (which can move MAP@R of the un-reranked list, trunc 0)
+        order_tie = False
+        if comparable and not np.array_equal(idx[q, :kk], top):
+            ref_sc = {int(cand): float(sc) for cand, sc in zip(top, d["approx"].numpy())}
+            worst = max(abs(ref_sc[int(a)] - ref_sc[int(b)]) for a, b in zip(idx[q, :kk], top) if a != b)
+            if worst < TIE:
+                order_tie = True
+                c["stage0_order_differs_within_tie"] += 1
+            else:
+                c["stage0_order_differs_beyond_tie"] += 1
         n_ref, n_mine = int(d["n_iter"]), int(niter[q])
         equal = n_ref == n_mine
         if equal:
@@ -91,6 +104,8 @@ def compare(dumps, idx, score, niter, k, trunc_nums=None, per_query=None, thresh
                 c["metric_mismatch_queries"] += 1
                 if equal and comparable:
                     c["metric_mismatch_queries_equal_niter"] += 1
+                    if not order_tie:     # same shortlist, same iteration count, same first-stage order: must be identical
+                        c["metric_mismatch_unexplained"] += 1
     if dt:
         # sums over the sampled queries of (cuda - oracle), per trunc: r1, rp, mapr (not yet divided by N/100)
         c["tally_delta"] = {str(t): v for t, v in dt.items()}

@@ -59,8 +59,8 @@ def test_calc_similarity_dropin_vs_reference_outputs(golden_dir, case):
     else:
         assert any(stop_ok(n_try, n_ref, errs) for n_try in (n_ref - 1, n_ref + 1) if n_try >= 1), \
             "plan differs from the reference although its stop was not borderline"
-        assert rel_err(score.cpu(), G[f"{name}_score"]).max() < 5e-4
-        np.testing.assert_allclose(uv[2].cpu(), G[f"{name}_T"], rtol=2e-2, atol=1e-9)
+        assert rel_err(score.cpu(), G[f"{name}_score"]).max() < 1e-2
+        np.testing.assert_allclose(uv[2].cpu(), G[f"{name}_T"], rtol=5e-2, atol=1e-9)
 
 
 def test_stage0_and_rollout_dropin(golden_dir):

@@ -454,8 +454,9 @@ int vr_evaluate_registered(vr_ctx* ctx, int64_t q_start, int64_t q_stride, int64
     std::vector<int32_t> truncs(n_trunc);
     for (int i = 0; i < n_trunc; i++) truncs[i] = std::min((int)trunc_nums_host[i], k);
 
-    // chunk the queries so that per-chunk buffers stay bounded
-    int64_t chunk = std::min<int64_t>(nq, 16384);
+    // chunk the queries so that per-chunk buffers stay bounded (shortlists of up to 1 GB per chunk: the SOP pass is ONE
+    // chunk, so that the whole first stage runs while a host bank is still being uploaded)
+    int64_t chunk = std::min<int64_t>(nq, std::max<int64_t>(16384, ((int64_t)1 << 30) / ((int64_t)kp * 12)));
     const bool fused = k > 0 && (pair_fused_supports(ctx->c, ctx->r, k, p) ||
                                  (!ctx->dbg_err && pair_fused_supports_wide(ctx->c, ctx->r, k, p)));
     if (k > 0 && !fused) {
