@@ -273,6 +273,7 @@ def main():
         t_end.record()
         sync_all()
     launches = _lib.take_launch_count()
+    s0_stats = eng.stage0_stats()          # of the last timed step's first stage (rows redone by the exact fp32 fallback)
     elapsed_ms = t_begin.elapsed_time(t_end)
     t_el = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -347,6 +348,8 @@ def main():
                    "stage_ms": {"stage0_topk": s0_ms, "pair_kernel": pf_ms, "finalize_tally_d2h": fin_ms},
                    "metrics": {"r1": (tallies[:, 0] / scale).tolist(), "rp": (tallies[:, 1] / scale).tolist(),
                                "mapr": (tallies[:, 2] / scale).tolist()},
+                   "stage0": dict(s0_stats, path="tcgen05 GEMM + fused select (stage0_mma.cu)" if os.environ.get("VR_STAGE0", "") != "sgemm"
+                                  and c == 128 and nq >= 256 and kp <= 256 else "fp32 (stage0_topk.cu)"),
                    "sm_count": eng.sm_count, "pair_transport": os.environ.get("VR_PAIR_TRANSPORT", "global")},
         "roofline": {"bound": "hbm", "kernel": "pair_fused_kernel", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

@@ -109,7 +109,13 @@ VR_API int vr_num_pos(vr_ctx* ctx, const int64_t* labels, int64_t n, int32_t* nu
  * mask approx_sim[idx] = -100 (eval_cvt_diml.py:327) and the head of the full argsort
  * (:329-332): out_idx[i, :] are the kp best gallery indices of query i in descending
  * score order (ties: lower index first), out_score the matching fp32 scores; rows are
- * padded with idx -1 when n < kp.  The N x N score matrix is never written to memory.
+ * padded with idx -1 when n < kp.  For batches (>= 256 queries) over 128-d embeddings with
+ * kp <= 256 the scores are a tcgen05 GEMM whose accumulators are filtered as they leave
+ * tensor memory: the N x N score matrix is never written to memory, and the lists are
+ * bit-identical to the fp32 FMA-chain path (shortlist by the tensor-core score, canonical
+ * fp32 re-score, rounding-bound acceptance test, exact fallback for rows that fail it).
+ * A few queries take a fused fp32 kernel (no matrix in memory either); batches with other
+ * widths or longer shortlists write [rows, N] score chunks to the workspace.
  * Query i is gallery item q_start + i * q_stride (self-masked) when q_centers is NULL;
  * otherwise q_centers is [nq, c] and self_idx (nullable, int64 [nq]) names the gallery
  * item to mask for each query (the query != gallery case of training_tools/val.py:159-190). */
@@ -117,6 +123,11 @@ VR_API size_t vr_stage0_workspace_bytes(vr_ctx* ctx, int64_t nq, int32_t kp);
 VR_API int vr_stage0_topk(vr_ctx* ctx, const float* q_centers, const int64_t* self_idx, int64_t q_start,
                    int64_t q_stride, int64_t nq, int32_t kp, int32_t* out_idx, float* out_score,
                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* Counters of the last vr_stage0_topk call on this context (synchronises `stream`): out4[0] = rows the tensor-core path
+ * handed to its exact fp32 fallback, out4[3] = rows whose candidate buffer overflowed (a subset), out4[2] = 1 when the
+ * centres held values the fp16 split cannot represent (then every row is redone), out4[1] = bits of max |g|^2. */
+VR_API int vr_stage0_stats(vr_ctx* ctx, uint32_t* out4_host, void* stream);
 
 /* S2-S5a: structural scores of query/candidate pairs ------------------------------------
  * Replaces the stage-1 call at eval_cvt_diml.py:334-351 for a batch of queries taken from

@@ -220,7 +220,7 @@ int vr_bank_prepare(vr_ctx* ctx, int64_t first, int64_t count, void* stream) {
 
 size_t vr_stage0_workspace_bytes(vr_ctx* ctx, int64_t nq, int32_t kp) {
     if (!ctx || ctx->n <= 0) return 0;
-    return stage0_workspace_bytes(nq, ctx->n, kp, ctx->sms);
+    return stage0_workspace_bytes(nq, ctx->n, ctx->c, kp, ctx->sms);
 }
 
 int vr_stage0_topk(vr_ctx* ctx, const float* q_centers, const int64_t* self_idx, int64_t q_start, int64_t q_stride,
@@ -236,8 +236,23 @@ int vr_stage0_topk(vr_ctx* ctx, const float* q_centers, const int64_t* self_idx,
         VR_REQUIRE(q_start >= 0 && q_start + (nq - 1) * q_stride < ctx->n && q_start + (nq - 1) * q_stride >= 0,
                    "stage0: query range outside the gallery");
     VR_CHECK_CUDA(cudaSetDevice(ctx->device));
+    void* stats = nullptr;
+    int rc = arena_get(ctx, "s0_stats", 256, &stats);
+    if (rc) return rc;
     return stage0_topk(q_centers, self_idx, ctx->centers, q_start, q_stride, nq, ctx->n, ctx->c, kp, out_idx, out_score,
-                       workspace, workspace_bytes, ctx->sms, (cudaStream_t)stream);
+                       workspace, workspace_bytes, ctx->sms, (uint32_t*)stats, (cudaStream_t)stream);
+}
+
+int vr_stage0_stats(vr_ctx* ctx, uint32_t* out4_host, void* stream) {
+    VR_REQUIRE(ctx && out4_host, "stage0_stats: bad arguments");
+    VR_CHECK_CUDA(cudaSetDevice(ctx->device));
+    void* stats = nullptr;
+    int rc = arena_get(ctx, "s0_stats", 256, &stats);
+    if (rc) return rc;
+    VR_CHECK_CUDA(cudaMemcpyAsync(ctx->pinned + 4, stats, 16, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    VR_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    memcpy(out4_host, ctx->pinned + 4, 16);
+    return VR_OK;
 }
 
 size_t vr_rerank_workspace_bytes(vr_ctx* ctx, int64_t nq, int32_t k, const vr_ot_params* p) {
@@ -464,7 +479,7 @@ int vr_evaluate_registered(vr_ctx* ctx, int64_t q_start, int64_t q_stride, int64
         chunk = std::max<int64_t>(1, std::min<int64_t>(chunk, (int64_t)((size_t)1536 * 1024 * 1024 / per_q)));
     }
     void *d_idx, *d_sc, *d_ot, *d_nit, *d_tal, *d_ws0, *d_ws1, *d_ws2;
-    size_t ws0 = stage0_workspace_bytes(chunk, ctx->n, kp, ctx->sms);
+    size_t ws0 = stage0_workspace_bytes(chunk, ctx->n, ctx->c, kp, ctx->sms);
     size_t ws1 = k > 0 ? (fused ? 256 : generic_rerank_workspace_bytes(chunk, k, ctx->r, p)) : 256;
     size_t ws2 = finalize_workspace_bytes(chunk, n_trunc);
     if ((rc = arena_get(ctx, "ev_idx", (size_t)chunk * kp * 4, &d_idx))) return rc;

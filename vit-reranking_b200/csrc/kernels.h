@@ -57,10 +57,19 @@ struct GenArgs {
 };
 
 // stage0_topk.cu
-size_t stage0_workspace_bytes(int64_t nq, int64_t n, int kp, int sms);
+// stats_dev (nullable): 4 uint32 on the device = {rows redone by the exact fallback, max |g|^2 bits, unsplittable-value flag,
+// rows whose candidate buffer overflowed} of the tensor-core path; zeros for the fp32 paths
+size_t stage0_workspace_bytes(int64_t nq, int64_t n, int c, int kp, int sms);
 int stage0_topk(const float* q_centers, const int64_t* self_idx, const float* centers, int64_t q_start,
                 int64_t q_stride, int64_t nq, int64_t n, int c, int kp, int32_t* out_idx, float* out_score,
-                void* ws, size_t ws_bytes, int sms, cudaStream_t st);
+                void* ws, size_t ws_bytes, int sms, uint32_t* stats_dev, cudaStream_t st);
+
+// stage0_mma.cu
+bool stage0_mma_supported(int64_t nq, int64_t n, int c, int kp);
+size_t stage0_mma_workspace_bytes(int64_t nq, int64_t n, int kp, int sms);
+int stage0_mma_topk(const float* q_centers, const int64_t* self_idx, const float* centers, int64_t q_start, int64_t q_stride,
+                    int64_t nq, int64_t n, int kp, int32_t* out_idx, float* out_score, void* ws, size_t ws_bytes, int sms,
+                    uint32_t* stats_dev, cudaStream_t st);
 int global_similarity(const float* q, const float* centers, int64_t n, int c, float* sim, cudaStream_t st);
 
 // pair_fused.cu

@@ -1,16 +1,21 @@
-// S1: first-stage retrieval = fp32 cosine GEMM over the global embeddings fused with a
+// S1, fp32 paths: first-stage retrieval = fp32 cosine GEMM over the global embeddings with a
 // streaming per-query top-K' select.  Replaces calc_similarity(stage=0)
 // (utilities/diml.py:83-85), the self mask (evaluation/eval_cvt_diml.py:327) and the head
-// of the full argsort (:329-332).  The N x N score matrix never leaves the SM: every
-// BM x 64 score tile is filtered in registers against the per-row running threshold and
-// only survivors are appended to a per-row candidate buffer in shared memory, which one
-// warp re-sorts (bitonic) whenever it is about to overflow.
+// of the full argsort (:329-332).  Batches over 128-d embeddings take the tensor-core path of
+// stage0_mma.cu (score matrix in tensor memory only); this file is the canonical fp32 arithmetic
+// that path reproduces, and serves everything it does not cover:
+//   - a few queries (< 256): stage0_select_kernel, the select fused into the score tile (every BM x 64 tile
+//     is filtered in registers against the per-row running threshold; survivors go to a per-row buffer in
+//     shared memory that one warp re-sorts before it overflows); no score matrix in memory;
+//   - batches with other widths or shortlists beyond 256: stage0_scores_kernel writes a [rows, N] score
+//     chunk to the workspace (HBM) and stage0_rowselect_kernel streams each row once.
 //
 // Arithmetic: plain fp32 FMA, sequential over the C channels (no TF32: the top-K sets
 // must match the reference's fp32 path, SURVEY.md section 7 hard part 3).
 #include <algorithm>
 #include "common.cuh"
 #include "kernels.h"
+#include "stage0_select.cuh"
 
 namespace vr {
 
@@ -336,8 +341,6 @@ __global__ void stage0_rowselect_kernel(Stage0Args a, int64_t r_begin, int64_t r
     else if (!a.q_centers) self = a.q_start + g * a.q_stride;
     const float* srow = scores + r * ld;
     unsigned long long thr = 0ull;
-    int cnt = 0;
-    const unsigned lt = (1u << lane) - 1u;
     if (M > 0) {
         uint32_t top[M > 0 ? M : 1];   // this lane's best ordered scores, descending
 #pragma unroll
@@ -376,53 +379,7 @@ __global__ void stage0_rowselect_kernel(Stage0Args a, int64_t r_begin, int64_t r
         const unsigned long long t0key = (unsigned long long)t0 << 32;     // the smallest key with that score
         thr = t0key ? t0key - 1ull : 0ull;                                // pass 2 keeps key > thr, i.e. key >= t0key
     }
-    // 256 scores per step, as four groups of 64 (the buffer check is per group); the next step's loads are in flight
-    // while this one is filtered, so the L2 / HBM latency is paid once per row, not once per group
-    auto load4 = [&](float2 (&d)[4], int64_t base) {
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int64_t col0 = base + 64 * u + 2 * lane;
-            d[u] = make_float2(0.f, 0.f);
-            if (col0 < ld) d[u] = __ldcs(reinterpret_cast<const float2*>(srow + col0));   // ld is even: col0 + 1 < ld too
-        }
-    };
-    float2 cur[4], nxt[4];
-    load4(cur, 0);
-    for (int64_t base = 0; base < a.n; base += 256) {
-        if (base + 256 < a.n) load4(nxt, base + 256);
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            if (base + 64 * u >= a.n) break;
-            if (cnt > P - 64) {
-                for (int e = cnt + lane; e < P; e += 32) b[e] = 0ull;
-                warp_bitonic_sort_desc(b, P, lane);
-                cnt = min(cnt, kp);
-                if (cnt >= kp) thr = b[kp - 1];
-                __syncwarp();
-            }
-            const int64_t col0 = base + 64 * u + 2 * lane;
-#pragma unroll
-            for (int t = 0; t < 2; t++) {
-                const int64_t col = col0 + t;
-                float s = t ? cur[u].y : cur[u].x;
-                if (col == self) s = -100.0f;
-                const unsigned long long key = pack_key(s, (uint32_t)col);
-                const bool take = col < a.n && key > thr;
-                const unsigned m = __ballot_sync(0xffffffffu, take);
-                if (take) b[cnt + __popc(m & lt)] = key;
-                cnt += __popc(m);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) cur[u] = nxt[u];
-    }
-    for (int e = cnt + lane; e < P; e += 32) b[e] = 0ull;
-    warp_bitonic_sort_desc(b, P, lane);
-    for (int e = lane; e < kp; e += 32) {
-        const unsigned long long key = b[e];
-        a.out_idx[g * kp + e] = key ? (int32_t)key_index(key) : -1;
-        a.out_score[g * kp + e] = key ? key_score(key) : 0.f;
-    }
+    warp_rowselect_stream(srow, a.n, ld, self, kp, P, b, lane, thr, a.out_idx + g * kp, a.out_score + g * kp);
 }
 
 // Merge the nsplit partial shortlists of every query (one warp per query).
@@ -523,9 +480,11 @@ static Stage0GemmPlan plan_stage0_gemm(int64_t nq, int64_t n, int kp) {
     return g;
 }
 
-size_t stage0_workspace_bytes(int64_t nq, int64_t n, int kp, int sms) {
+size_t stage0_workspace_bytes(int64_t nq, int64_t n, int c, int kp, int sms) {
     const size_t fused = plan_stage0(nq, n, kp, sms).ws_bytes, gemm = plan_stage0_gemm(nq, n, kp).ws_bytes;
-    return align_up(std::max(fused, gemm), 256) + 256;
+    const size_t mma = stage0_mma_supported(nq, n, c, kp) ? stage0_mma_workspace_bytes(nq, n, kp, sms) : 0;
+    // the tensor-core path, when it applies, is the only one that runs: its workspace alone decides
+    return align_up(mma ? mma : std::max(fused, gemm), 256) + 256;
 }
 
 template <int BM, int TY, int TX>
@@ -540,12 +499,18 @@ static int launch_select(const Stage0Args& a, const Stage0Plan& pl, cudaStream_t
 
 int stage0_topk(const float* q_centers, const int64_t* self_idx, const float* centers, int64_t q_start,
                 int64_t q_stride, int64_t nq, int64_t n, int c, int kp, int32_t* out_idx, float* out_score,
-                void* ws, size_t ws_bytes, int sms, cudaStream_t st) {
+                void* ws, size_t ws_bytes, int sms, uint32_t* stats_dev, cudaStream_t st) {
     VR_REQUIRE(nq > 0 && n > 0 && kp > 0, "stage0: empty problem (nq=%lld n=%lld kp=%d)", (long long)nq,
                (long long)n, kp);
     VR_REQUIRE(c % 4 == 0, "stage0: embed dim %d must be a multiple of 4", c);
     VR_REQUIRE(kp <= 1984, "stage0: shortlist length %d exceeds 1984", kp);
     VR_REQUIRE(n < 0xffffffffll, "stage0: gallery too large");
+    // batches over 128-d embeddings: tcgen05 GEMM with the select fused into the accumulator read-out (stage0_mma.cu),
+    // bit-identical lists; the score matrix is never written to memory
+    if (stage0_mma_supported(nq, n, c, kp))
+        return stage0_mma_topk(q_centers, self_idx, centers, q_start, q_stride, nq, n, kp, out_idx, out_score, ws, ws_bytes, sms,
+                               stats_dev, st);
+    if (stats_dev) VR_CHECK_CUDA(cudaMemsetAsync(stats_dev, 0, 16, st));
     Stage0Plan pl = plan_stage0(nq, n, kp, sms);
     if (pl.smem > 227 * 1024) {
         set_error("stage0: shortlist %d needs %zu B of shared memory", kp, pl.smem);

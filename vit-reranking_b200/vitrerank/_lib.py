@@ -44,6 +44,7 @@ def _load():
         "vr_num_pos": (C.c_int, [vp, vp, i64, vp, P(i32), vp]),
         "vr_stage0_workspace_bytes": (sz, [vp, i64, i32]),
         "vr_stage0_topk": (C.c_int, [vp, vp, vp, i64, i64, i64, i32, vp, vp, vp, sz, vp]),
+        "vr_stage0_stats": (C.c_int, [vp, P(C.c_uint32), vp]),
         "vr_rerank_workspace_bytes": (sz, [vp, i64, i32, P(OTParamsStruct)]),
         "vr_rerank_scores": (C.c_int, [vp, i64, i64, i64, i32, vp, i32, P(OTParamsStruct), vp, vp, vp, sz, vp]),
         "vr_finalize_workspace_bytes": (sz, [vp, i64, i32]),

@@ -204,6 +204,13 @@ class RerankEngine:
                                  _ptr(score), _ptr(ws), ws.numel(), _stream(self.device)), "vr_stage0_topk")
         return idx, score
 
+    def stage0_stats(self):
+        """Counters of the last stage0_topk call (synchronises): rows the tensor-core path handed to its exact fp32
+        fallback, rows whose candidate buffer overflowed, whether the centres held values the fp16 split cannot hold."""
+        out = (C.c_uint32 * 4)()
+        check(lib.vr_stage0_stats(self._h, out, _stream(self.device)), "vr_stage0_stats")
+        return {"fallback_rows": int(out[0]), "overflow_rows": int(out[3]), "unsplittable": int(out[2])}
+
     # ---- S2-S5a ----------------------------------------------------------------------------
     def rerank_scores(self, cand_idx, k, params: OTParams, q_start=0, q_stride=1):
         cand_idx = cand_idx.to(device=self.device, dtype=torch.int32).contiguous()
