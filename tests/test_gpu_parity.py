@@ -356,6 +356,42 @@ def test_wide_shortlists_fused(eng, n, k, flags, nq):
         np.testing.assert_allclose(tal[:, col] / scale, ref0[key], rtol=0, atol=flips / scale + 1e-9)
 
 
+@pytest.mark.parametrize("n,k,flags,nq", [
+    (400, 100, dict(use_rollout=True, ot_part=0.5), 12),
+    (400, 100, dict(use_minus=True, ot_part=0.1), 12),
+    (260, 37, dict(use_inverse=True, temperature=0.1, use_cls_token=True, ot_part=0.9), 13),
+    (300, 112, dict(use_uniform=True, ot_part=0.6), 6),
+])
+def test_partial_ot_fused(eng, n, k, flags, nq):
+    """Partial OT (one dummy point, diml.py:59-75) in the fused kernel -- the dummy row / column ride in the padding of
+    strip 12 -- against the generic solver (same arithmetic order: iteration counts equal, scores equal to rounding of the
+    tensor-core similarity) and against the oracle, un-forced."""
+    from vitrerank.engine import OTParams
+    g = synth.make_gallery(n, 128, 49, classes=max(3, n // 50), seed=n + k, sigma=0.6)
+    stride = n // nq
+    ids = list(range(0, n, stride))[:nq]
+    p = OTParams.from_flags(**flags)
+    eng.register(g.patches, g.centers, g.rollout, g.labels)
+    idx, approx = eng.stage0_topk(k, q_start=0, q_stride=stride, nq=nq)
+    score, niter = eng.rerank_scores(idx, k, p, q_start=0, q_stride=stride)          # fused (scores only)
+    eng.err_trace(nq)                                                                 # a diagnostics output: generic solver
+    try:
+        score_g, niter_g = eng.rerank_scores(idx, k, p, q_start=0, q_stride=stride)
+    finally:
+        eng.err_trace(0)
+    idx, score, niter = idx.cpu().numpy(), score.cpu().numpy(), niter.cpu().numpy()
+    score_g, niter_g = score_g.cpu().numpy(), niter_g.cpu().numpy()
+    same = niter == niter_g
+    assert same.sum() >= nq - 1, (niter, niter_g)
+    assert rel_err(score[same], score_g[same]).max() < 2e-5
+    ref0 = O.evaluate_banks(g.patches, g.centers, g.rollout, g.labels, trunc_nums=[0, k], query_ids=ids, dump=True, **flags)
+    for q, d in enumerate(ref0["dump"]):
+        assert stop_ok(int(niter[q]), d["n_iter"], d["errs"]), (q, int(niter[q]), d["n_iter"], d["errs"][-3:])
+        pos = {int(c): i for i, c in enumerate(idx[q])}
+        mine = np.array([score[q, pos[int(c)]] for c in d["top"]])
+        assert rel_err(mine, d["score"].numpy()).max() < score_gate(niter[q], d["n_iter"]), q
+
+
 def test_evaluate_stages_and_scores(eng):
     """Stage by stage on one gallery: shortlist sets, per-pair scores, reranked order."""
     from vitrerank.engine import OTParams

@@ -257,7 +257,7 @@ int vr_stage0_stats(vr_ctx* ctx, uint32_t* out4_host, void* stream) {
 
 size_t vr_rerank_workspace_bytes(vr_ctx* ctx, int64_t nq, int32_t k, const vr_ot_params* p) {
     if (!ctx || !p || ctx->n <= 0) return 0;
-    if (pair_fused_supports(ctx->c, ctx->r, k, p) || (!ctx->dbg_err && pair_fused_supports_wide(ctx->c, ctx->r, k, p))) return 256;
+    if (pair_fused_supports(ctx->c, ctx->r, k, p, !ctx->dbg_err) || (!ctx->dbg_err && pair_fused_supports_wide(ctx->c, ctx->r, k, p))) return 256;
     return generic_rerank_workspace_bytes(nq, k, ctx->r, p);
 }
 
@@ -282,7 +282,7 @@ int vr_rerank_scores(vr_ctx* ctx, int64_t q_start, int64_t q_stride, int64_t nq,
         ctx->pending_wait = false;
     }
     // (the err trace of vr_debug_err_trace is a diagnostics output: shortlists beyond 112 then take the generic solver)
-    if (pair_fused_supports(ctx->c, ctx->r, k, p) || (!ctx->dbg_err && pair_fused_supports_wide(ctx->c, ctx->r, k, p))) {
+    if (pair_fused_supports(ctx->c, ctx->r, k, p, !ctx->dbg_err) || (!ctx->dbg_err && pair_fused_supports_wide(ctx->c, ctx->r, k, p))) {
         PairArgs a{};
         a.q_patches = ctx->patches;
         a.q_centers = ctx->centers;
@@ -386,7 +386,7 @@ int vr_calc_similarity(vr_ctx* ctx, const float* anchor, const float* anchor_cen
     VR_REQUIRE(p->mode != VR_MODE_ROLLOUT || (q_rollout && c_rollout), "calc_similarity: rollout marginals missing");
     VR_CHECK_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
-    if (pair_fused_supports(c, r, (int)n, p) && ((uintptr_t)anchor & 15) == 0 && ((uintptr_t)fb & 15) == 0) {
+    if (pair_fused_supports(c, r, (int)n, p, false) && ((uintptr_t)anchor & 15) == 0 && ((uintptr_t)fb & 15) == 0) {
         PairArgs a{};
         a.q_patches = anchor;
         a.q_centers = anchor_center;
@@ -472,7 +472,7 @@ int vr_evaluate_registered(vr_ctx* ctx, int64_t q_start, int64_t q_stride, int64
     // chunk the queries so that per-chunk buffers stay bounded (shortlists of up to 1 GB per chunk: the SOP pass is ONE
     // chunk, so that the whole first stage runs while a host bank is still being uploaded)
     int64_t chunk = std::min<int64_t>(nq, std::max<int64_t>(16384, ((int64_t)1 << 30) / ((int64_t)kp * 12)));
-    const bool fused = k > 0 && (pair_fused_supports(ctx->c, ctx->r, k, p) ||
+    const bool fused = k > 0 && (pair_fused_supports(ctx->c, ctx->r, k, p, !ctx->dbg_err) ||
                                  (!ctx->dbg_err && pair_fused_supports_wide(ctx->c, ctx->r, k, p)));
     if (k > 0 && !fused) {
         size_t per_q = generic_rerank_workspace_bytes(1, k, ctx->r, p);

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(GP_THREADS) generic_prepare_kernel(GenArgs a) 
     const int C = a.c, R = a.r;
     const bool full = a.p.ot_part > 0.999f;
     const int Re = full ? R : R + 1;
-    const float bins = 1.0f - a.p.ot_part;
+    const float bins = a.part_bin;   // 1 - ot_part, rounded as the reference rounds it (partial_ot_bin)
     const int mode = a.p.mode;
     if (pi == 0 && tid == 0) {
         a.done[qi] = 0;
@@ -471,6 +471,7 @@ int generic_rerank(GenArgs a, void* ws, size_t ws_bytes, cudaStream_t st) {
     const int64_t np = a.nq * a.k;
     VR_REQUIRE(np < 0x7fffffffll, "generic_rerank: too many pairs in one call (%lld)", (long long)np);
     const int re = (a.p.ot_part > 0.999f) ? a.r : a.r + 1;
+    a.part_bin = partial_ot_bin(a.p.ot_part);
     GenWs w = carve(ws, a.nq, np, a.r, re, re, true);
     if (w.bytes > ws_bytes) {
         set_error("generic_rerank: workspace %zu < %zu", ws_bytes, w.bytes);

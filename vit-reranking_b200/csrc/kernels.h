@@ -23,6 +23,7 @@ struct PairArgs {
     long long* dbg_clk;       // optional [nq, 16]: phase clocks (only read by builds with -DPR_TIMING)
     unsigned long long* ex_part;   // exchange buffer of the global transport (set by pair_fused_launch)
     int group_ctas;           // CTAs per query of the wide path, ceil(k / 16) (set by pair_fused_launch)
+    float part_bin;           // partial OT: 1 - ot_part as the reference rounds it (set by pair_fused_launch)
     const void* c_packed_a;   // re-packed candidate bank (pair_fused_repack) or nullptr: convert on the fly
     const void* q_packed_b;   // re-packed query bank, indexed by the query id
 };
@@ -39,6 +40,7 @@ struct GenArgs {
     int64_t q_start, q_stride, nq;
     int k, c, r;
     vr_ot_params p;
+    float part_bin;   // 1 - ot_part as the reference rounds it (set by generic_rerank)
     // workspace
     float* sim;    // [np, r, r]
     float* K;      // [np, re, re]
@@ -74,7 +76,8 @@ int global_similarity(const float* q, const float* centers, int64_t n, int c, fl
 
 // pair_fused.cu
 int pair_fused_max_clusters(int* out);
-bool pair_fused_supports(int c, int r, int k, const vr_ot_params* p);
+bool pair_fused_supports(int c, int r, int k, const vr_ot_params* p, bool scores_only);
+float partial_ot_bin(float ot_part);   // 1 - ot_part rounded as diml.py:61 rounds it
 bool pair_fused_supports_wide(int c, int r, int k, const vr_ot_params* p);   // 112 < k <= 1024, scores only
 int pair_fused_launch(const PairArgs& a, int64_t nq, cudaStream_t st);
 int pair_fused_ctx_open(int device);    // vr_create / vr_destroy: the last context on a device frees the exchange buffer
