@@ -97,6 +97,21 @@ VR_API int vr_bank_register(vr_ctx* ctx, const float* patches, const float* cent
  * rerank calls must be ordered after it by the caller (same stream or an event).  No-op for shapes without a fused kernel. */
 VR_API int vr_bank_prepare(vr_ctx* ctx, int64_t first, int64_t count, void* stream);
 
+/* Bank ingest: the step between the backbone and the path (evaluation/eval_cvt_diml.py:269-278 head output -> permute ->
+ * AdaptiveAvgPool2d(grid_size); :304 F.normalize(feature_bank, dim=1); :305 F.normalize(feature_bank_center, dim=1)).
+ * tokens: [count, h * w, C] (channel_major = 0: the head projection's output) or [count, C, h * w] (channel_major = 1: the
+ * feature maps of the trained-model branch :286-289); centers_raw (nullable): [count, C] un-normalised global embeddings.
+ * Writes rows [first, first + count) of the REGISTERED patch / centre banks (they are the destination: register the empty
+ * buffers first; h, w must be whole multiples of the registered grid) and, for 128 x 49 banks, the library's operand copy
+ * of those images, so no later re-pack pass is needed (ascending ranges without gaps, like vr_bank_prepare).  The results
+ * equal torch's CPU AdaptiveAvgPool2d + F.normalize bit for bit. */
+VR_API int vr_bank_ingest(vr_ctx* ctx, const float* tokens, const float* centers_raw, int32_t channel_major, int64_t first,
+                          int64_t count, int32_t h, int32_t w, void* stream);
+
+/* Attaches labels / class counts (device, [n]) to the registered bank without touching the banks or the operand copy
+ * (for banks filled by vr_bank_ingest, whose labels arrive with the batches). */
+VR_API int vr_bank_labels(vr_ctx* ctx, const int64_t* labels, const int32_t* num_pos);
+
 /* num_pos[i] = #{j : labels[j] == labels[i]}: the `num_pos = torch.sum(gallery_label == query_label)` of
  * evaluation/metrics.py:34 for every gallery item at once (device int32 [n]; counts the item itself).  When
  * max_num_pos_host is not NULL the call synchronises `stream` and stores the largest count there (the first-stage
@@ -144,6 +159,13 @@ VR_API int vr_rerank_scores(vr_ctx* ctx, int64_t q_start, int64_t q_stride, int6
                      float* out_score, int32_t* out_niter, void* workspace, size_t workspace_bytes,
                      void* stream);
 
+/* The same for queries that are NOT gallery items (training_tools/val.py:159-190: MSLS query images against the database
+ * images of a city): q_patches [nq, c, r], q_centers [nq, c] (cc modes with use_cls_token), q_rollout [nq, r] (rollout mode);
+ * candidates come from the registered bank.  Pair with vr_stage0_topk(q_centers, self_idx = NULL). */
+VR_API int vr_rerank_scores_queries(vr_ctx* ctx, const float* q_patches, const float* q_centers, const float* q_rollout,
+                             int64_t nq, int32_t k, const int32_t* cand_idx, int32_t cand_stride, const vr_ot_params* p,
+                             float* out_score, int32_t* out_niter, void* workspace, size_t workspace_bytes, void* stream);
+
 /* S5b: blend, re-sort, metrics --------------------------------------------------------
  * Replaces eval_cvt_diml.py:357-372 and evaluation/metrics.py:26-47 for a batch of
  * queries: total = ot_score + approx_score, descending argsort (NaN first, ties: lower
@@ -158,6 +180,11 @@ VR_API int vr_finalize(vr_ctx* ctx, int64_t q_start, int64_t q_stride, int64_t n
                 const int32_t* approx_idx, const float* approx_score, const float* ot_score,
                 const int32_t* trunc_nums_host, int32_t n_trunc, int32_t* out_rank, double* tallies,
                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* The blend + re-sort alone (eval_cvt_diml.py:357, training_tools/val.py:197): out_rank[q, :] = approx_idx[q, rank] with
+ * rank = argsort(ot_score[q] + approx_score[q, :k], descending) (NaN first, ties: lower position first).  No labels needed. */
+VR_API int vr_blend_rank(vr_ctx* ctx, int64_t nq, int32_t k, int32_t kp, const int32_t* approx_idx, const float* approx_score,
+                  const float* ot_score, int32_t* out_rank, void* stream);
 
 /* Direct calls (the per-call surface of utilities/diml.py) ------------------------------
  * vr_sinkhorn replaces Sinkhorn(K, u, v, iter) (diml.py:42-54) for any [b, m, n] batch:

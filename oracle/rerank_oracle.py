@@ -215,7 +215,7 @@ def recall_at(tops, query_label, labels, ks=(1, 2, 4, 8)):
 def evaluate_banks(patches, centers, rollout, labels, trunc_nums=None, use_rollout=False,
                    use_uniform=False, use_inverse=False, temperature=1.0,
                    use_cls_token=False, use_minus=False, ot_part=0.1, query_ids=None,
-                   dump=False, force_iters=None):
+                   dump=False, force_iters=None, use_soft=False):
     """The per-query loop of eval_cvt_diml.py:308-372 + :402-416 over pre-built banks.
 
     Branch selection follows :201,334-351: with use_rollout the rollout branch runs and
@@ -237,7 +237,8 @@ def evaluate_banks(patches, centers, rollout, labels, trunc_nums=None, use_rollo
     recall = {t: [0.0, 0.0, 0.0, 0.0] for t in trunc_nums}
     kmax = max(trunc_nums)
     dumps = []
-    mode = "rollout" if use_rollout else select_mode(use_uniform, use_inverse, use_minus)
+    # (use_soft: the flag of the sibling loops evaluation/eval_attn_diml.py:219-273 / eval_swin_diml.py:241-271)
+    mode = "rollout" if use_rollout else select_mode(use_uniform, use_inverse, use_minus, use_soft)
     if use_rollout and use_uniform:
         mode = "uniform"
     for qpos, idx in enumerate(qids):

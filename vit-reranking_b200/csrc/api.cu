@@ -218,6 +218,47 @@ int vr_bank_prepare(vr_ctx* ctx, int64_t first, int64_t count, void* stream) {
     return VR_OK;
 }
 
+int vr_bank_labels(vr_ctx* ctx, const int64_t* labels, const int32_t* num_pos) {
+    VR_REQUIRE(ctx, "ctx is null");
+    if (!ctx->patches) {
+        set_error("bank_labels: no bank registered");
+        return VR_E_NOBANK;
+    }
+    ctx->labels = labels;
+    ctx->num_pos = num_pos;
+    return VR_OK;
+}
+
+int vr_bank_ingest(vr_ctx* ctx, const float* tokens, const float* centers_raw, int32_t channel_major, int64_t first,
+                   int64_t count, int32_t h, int32_t w, void* stream) {
+    VR_REQUIRE(ctx, "ctx is null");
+    if (!ctx->patches) {
+        set_error("bank_ingest: register the (empty) destination banks first");
+        return VR_E_NOBANK;
+    }
+    int grid = 1;
+    while (grid * grid < ctx->r) grid++;
+    VR_REQUIRE(grid * grid == ctx->r, "bank_ingest: the registered bank has %d patches per image, not a square grid", ctx->r);
+    VR_REQUIRE(tokens && count > 0 && first >= 0 && first + count <= ctx->n, "bank_ingest: range [%lld, %lld) outside the bank",
+               (long long)first, (long long)(first + count));
+    VR_CHECK_CUDA(cudaSetDevice(ctx->device));
+    void* packed = nullptr;
+    const bool fused_shape = ctx->c == 128 && ctx->r == 49;
+    if (fused_shape) {
+        VR_REQUIRE(first <= ctx->packed_hi, "bank_ingest: ranges must be ingested in ascending order without gaps");
+        int rc = arena_get(ctx, "packed", pair_fused_packed_bytes(ctx->n), &packed);
+        if (rc) return rc;
+    }
+    int rc = bank_ingest(tokens, centers_raw, channel_major, ctx->n, first, count, h, w, grid, ctx->c, const_cast<float*>(ctx->patches),
+                         centers_raw ? const_cast<float*>(ctx->centers) : nullptr, packed, (cudaStream_t)stream);
+    if (rc) return rc;
+    if (fused_shape) {
+        ctx->packed_hi = std::max(ctx->packed_hi, first + count);
+        if (ctx->packed_hi >= ctx->n) ctx->packed_valid = true;
+    }
+    return VR_OK;
+}
+
 size_t vr_stage0_workspace_bytes(vr_ctx* ctx, int64_t nq, int32_t kp) {
     if (!ctx || ctx->n <= 0) return 0;
     return stage0_workspace_bytes(nq, ctx->n, ctx->c, kp, ctx->sms);
@@ -261,9 +302,12 @@ size_t vr_rerank_workspace_bytes(vr_ctx* ctx, int64_t nq, int32_t k, const vr_ot
     return generic_rerank_workspace_bytes(nq, k, ctx->r, p);
 }
 
-int vr_rerank_scores(vr_ctx* ctx, int64_t q_start, int64_t q_stride, int64_t nq, int32_t k, const int32_t* cand_idx,
-                     int32_t cand_stride, const vr_ot_params* p, float* out_score, int32_t* out_niter,
-                     void* workspace, size_t workspace_bytes, void* stream) {
+// Queries either from the registered bank (q_* null: items q_start + i * q_stride) or from explicit banks [nq, ...]
+// (the query != gallery case of training_tools/val.py:159-190).
+static int rerank_scores_impl(vr_ctx* ctx, const float* q_patches, const float* q_centers, const float* q_rollout, int64_t q_start,
+                              int64_t q_stride, int64_t nq, int32_t k, const int32_t* cand_idx, int32_t cand_stride,
+                              const vr_ot_params* p, float* out_score, int32_t* out_niter, void* workspace, size_t workspace_bytes,
+                              void* stream) {
     VR_REQUIRE(ctx, "ctx is null");
     if (!ctx->patches) {
         set_error("rerank: no bank registered");
@@ -271,10 +315,13 @@ int vr_rerank_scores(vr_ctx* ctx, int64_t q_start, int64_t q_stride, int64_t nq,
     }
     int rc = check_params(p);
     if (rc) return rc;
+    const bool ext = q_patches != nullptr;
     VR_REQUIRE(nq > 0 && k > 0 && cand_idx && out_score && cand_stride >= k, "rerank: bad arguments");
-    VR_REQUIRE(p->mode != VR_MODE_ROLLOUT || ctx->rollout, "rerank: rollout mode needs a rollout bank");
-    VR_REQUIRE(q_start >= 0 && q_start + (nq - 1) * q_stride < ctx->n && q_start + (nq - 1) * q_stride >= 0,
-               "rerank: query range outside the gallery");
+    VR_REQUIRE(p->mode != VR_MODE_ROLLOUT || (ctx->rollout && (!ext || q_rollout)), "rerank: rollout mode needs the rollout banks");
+    VR_REQUIRE(!(ext && p->mode >= VR_MODE_INVERSE && p->use_cls_token && !q_centers), "rerank: query centres missing");
+    if (!ext)
+        VR_REQUIRE(q_start >= 0 && q_start + (nq - 1) * q_stride < ctx->n && q_start + (nq - 1) * q_stride >= 0,
+                   "rerank: query range outside the gallery");
     VR_CHECK_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     if (ctx->pending_wait) {   // vr_evaluate_host: the patch bank is still being uploaded on the copy stream
@@ -284,16 +331,16 @@ int vr_rerank_scores(vr_ctx* ctx, int64_t q_start, int64_t q_stride, int64_t nq,
     // (the err trace of vr_debug_err_trace is a diagnostics output: shortlists beyond 112 then take the generic solver)
     if (pair_fused_supports(ctx->c, ctx->r, k, p, !ctx->dbg_err) || (!ctx->dbg_err && pair_fused_supports_wide(ctx->c, ctx->r, k, p))) {
         PairArgs a{};
-        a.q_patches = ctx->patches;
-        a.q_centers = ctx->centers;
-        a.q_rollout = ctx->rollout;
+        a.q_patches = ext ? q_patches : ctx->patches;
+        a.q_centers = ext ? q_centers : ctx->centers;
+        a.q_rollout = ext ? q_rollout : ctx->rollout;
         a.c_patches = ctx->patches;
         a.c_centers = ctx->centers;
         a.c_rollout = ctx->rollout;
         a.cand_idx = cand_idx;
         a.cand_stride = cand_stride;
-        a.q_start = q_start;
-        a.q_stride = q_stride;
+        a.q_start = ext ? 0 : q_start;
+        a.q_stride = ext ? 1 : q_stride;
         a.k = k;
         a.p = *p;
         a.out_score = out_score;
@@ -309,19 +356,25 @@ int vr_rerank_scores(vr_ctx* ctx, int64_t q_start, int64_t q_stride, int64_t nq,
         }
         a.c_packed_a = packed;
         a.q_packed_b = (const char*)packed + pair_fused_packed_bytes(ctx->n) / 2;
+        if (ext) {   // explicit query bank: its operand planes are derived per call
+            void* packed_q = nullptr;
+            if ((rc = arena_get(ctx, "packed_q", pair_fused_packed_bytes(nq), &packed_q))) return rc;
+            if ((rc = pair_fused_repack(q_patches, nq, 0, nq, packed_q, st))) return rc;
+            a.q_packed_b = (const char*)packed_q + pair_fused_packed_bytes(nq) / 2;
+        }
         return pair_fused_launch(a, nq, st);
     }
     GenArgs g{};
-    g.q_patches = ctx->patches;
-    g.q_centers = ctx->centers;
-    g.q_rollout = ctx->rollout;
+    g.q_patches = ext ? q_patches : ctx->patches;
+    g.q_centers = ext ? q_centers : ctx->centers;
+    g.q_rollout = ext ? q_rollout : ctx->rollout;
     g.c_patches = ctx->patches;
     g.c_centers = ctx->centers;
     g.c_rollout = ctx->rollout;
     g.cand_idx = cand_idx;
     g.cand_stride = cand_stride;
-    g.q_start = q_start;
-    g.q_stride = q_stride;
+    g.q_start = ext ? 0 : q_start;
+    g.q_stride = ext ? 1 : q_stride;
     g.nq = nq;
     g.k = k;
     g.c = ctx->c;
@@ -331,6 +384,22 @@ int vr_rerank_scores(vr_ctx* ctx, int64_t q_start, int64_t q_stride, int64_t nq,
     g.out_niter = out_niter;
     g.dbg_err = ctx->dbg_err;
     return generic_rerank(g, workspace, workspace_bytes, st);
+}
+
+int vr_rerank_scores(vr_ctx* ctx, int64_t q_start, int64_t q_stride, int64_t nq, int32_t k, const int32_t* cand_idx,
+                     int32_t cand_stride, const vr_ot_params* p, float* out_score, int32_t* out_niter,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+    return rerank_scores_impl(ctx, nullptr, nullptr, nullptr, q_start, q_stride, nq, k, cand_idx, cand_stride, p, out_score,
+                              out_niter, workspace, workspace_bytes, stream);
+}
+
+int vr_rerank_scores_queries(vr_ctx* ctx, const float* q_patches, const float* q_centers, const float* q_rollout, int64_t nq,
+                             int32_t k, const int32_t* cand_idx, int32_t cand_stride, const vr_ot_params* p, float* out_score,
+                             int32_t* out_niter, void* workspace, size_t workspace_bytes, void* stream) {
+    VR_REQUIRE(q_patches, "rerank: query patches missing");
+    VR_REQUIRE(((uintptr_t)q_patches & 15) == 0, "rerank: query banks must be 16-byte aligned");
+    return rerank_scores_impl(ctx, q_patches, q_centers, q_rollout, 0, 1, nq, k, cand_idx, cand_stride, p, out_score, out_niter,
+                              workspace, workspace_bytes, stream);
 }
 
 size_t vr_finalize_workspace_bytes(vr_ctx* ctx, int64_t nq, int32_t n_trunc) {
@@ -351,6 +420,13 @@ int vr_finalize(vr_ctx* ctx, int64_t q_start, int64_t q_stride, int64_t nq, int3
     VR_CHECK_CUDA(cudaSetDevice(ctx->device));
     return finalize(q_start, q_stride, nq, k, kp, approx_idx, approx_score, ot_score, ctx->labels, ctx->num_pos,
                     trunc_nums_host, n_trunc, out_rank, tallies, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int vr_blend_rank(vr_ctx* ctx, int64_t nq, int32_t k, int32_t kp, const int32_t* approx_idx, const float* approx_score,
+                  const float* ot_score, int32_t* out_rank, void* stream) {
+    VR_REQUIRE(ctx, "ctx is null");
+    VR_CHECK_CUDA(cudaSetDevice(ctx->device));
+    return blend_rank(nq, k, kp, approx_idx, approx_score, ot_score, out_rank, (cudaStream_t)stream);
 }
 
 size_t vr_sinkhorn_workspace_bytes(int64_t b, int32_t m, int32_t n) { return generic_sinkhorn_workspace_bytes(b, m, n); }

@@ -44,8 +44,8 @@ __global__ void __launch_bounds__(FN_WARPS * 32) finalize_kernel(FinalizeArgs a)
     const int64_t qid = a.q_start + qi * a.q_stride;
     const int32_t* aidx = a.approx_idx + qi * kp;
     const float* asc = a.approx_score + qi * kp;
-    const int64_t ql = a.labels[qid];
-    const int np = a.num_pos[qid];
+    const int64_t ql = a.labels ? a.labels[qid] : 0;
+    const int np = a.labels ? a.num_pos[qid] : 0;
 
     // number of valid shortlist entries (rows are padded with -1 when the gallery is small)
     int nvalid = 0;
@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(FN_WARPS * 32) finalize_kernel(FinalizeArgs a)
     __syncwarp();
     if (a.out_rank)
         for (int e = lane; e < k; e += 32) a.out_rank[qi * k + e] = e < keff ? rer[e] : -1;
+    if (!a.labels) return;   // blend_rank: the reranked order only
 
     // ---- metrics per trunc (metrics.py:26-47) ----
     const int upto = min(np, nvalid);
@@ -264,6 +265,29 @@ int finalize(int64_t q_start, int64_t q_stride, int64_t nq, int k, int kp, const
     finalize_kernel<<<(unsigned)((nq + FN_WARPS - 1) / FN_WARPS), FN_WARPS * 32, smem, st>>>(a);
     VR_LAUNCH_CHECK();
     tally_kernel<<<n_trunc * FN_METRICS, 256, 0, st>>>(a.per_query, nq, n_trunc * FN_METRICS, tallies);
+    VR_LAUNCH_CHECK();
+    return VR_OK;
+}
+
+// eval_cvt_diml.py:357 / training_tools/val.py:197 alone: rank = argsort(ot_score + approx_score[:, :k], descending)
+// (ties: lower position first), out_rank[q, :] = approx_idx[q, rank].  No labels, no metrics.
+int blend_rank(int64_t nq, int k, int kp, const int32_t* approx_idx, const float* approx_score, const float* ot_score,
+               int32_t* out_rank, cudaStream_t st) {
+    VR_REQUIRE(nq > 0 && k >= 1 && k <= kp && approx_idx && approx_score && ot_score && out_rank, "blend_rank: bad arguments");
+    FinalizeArgs a{};
+    a.q_stride = 1;
+    a.nq = nq;
+    a.k = k;
+    a.kp = kp;
+    a.approx_idx = approx_idx;
+    a.approx_score = approx_score;
+    a.ot_score = ot_score;
+    a.out_rank = out_rank;
+    size_t smem = (size_t)FN_WARPS * k * (8 + 4) + (size_t)FN_WARPS * kp * 4 + 16;
+    VR_REQUIRE(smem <= 200 * 1024, "blend_rank: k=%d too large", k);
+    if (smem > 48 * 1024)
+        VR_CHECK_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    finalize_kernel<<<(unsigned)((nq + FN_WARPS - 1) / FN_WARPS), FN_WARPS * 32, smem, st>>>(a);
     VR_LAUNCH_CHECK();
     return VR_OK;
 }

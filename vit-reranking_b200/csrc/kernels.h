@@ -84,6 +84,8 @@ int pair_fused_ctx_open(int device);    // vr_create / vr_destroy: the last cont
 void pair_fused_ctx_close(int device);
 size_t pair_fused_packed_bytes(int64_t n);   // both roles
 int pair_fused_repack(const float* patches, int64_t n, int64_t first, int64_t count, void* packed, cudaStream_t st);
+int bank_ingest(const float* tokens, const float* centers_raw, int channel_major, int64_t n, int64_t first, int64_t count, int h,
+                int w, int grid, int c, float* patches, float* centers, void* packed, cudaStream_t st);
 
 // generic_ot.cu
 size_t generic_rerank_workspace_bytes(int64_t nq, int k, int r, const vr_ot_params* p);
@@ -98,6 +100,9 @@ int finalize(int64_t q_start, int64_t q_stride, int64_t nq, int k, int kp, const
              const float* approx_score, const float* ot_score, const int64_t* labels, const int32_t* num_pos,
              const int32_t* truncs, int n_trunc, int32_t* out_rank, double* tallies, void* ws, size_t ws_bytes,
              cudaStream_t st);
+
+int blend_rank(int64_t nq, int k, int kp, const int32_t* approx_idx, const float* approx_score, const float* ot_score,
+               int32_t* out_rank, cudaStream_t st);
 
 int num_pos_counts(const int64_t* labels, int64_t n, int32_t* num_pos, int32_t* max_dev, cudaStream_t st);
 

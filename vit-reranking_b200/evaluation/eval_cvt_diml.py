@@ -102,59 +102,89 @@ def evaluate_patch_similarity(model, dataset, dataloader):
 
 
 # ---- PHASE A: embed the test set into three HBM-resident banks [:225-305] ----------------------------
-def embed_banks(model, dataloader, training=False, grid_size=4, use_rollout=False, device=None):
+def embed_banks(model, dataloader, training=False, grid_size=4, use_rollout=False, device=None, n_total=None):
+    """The backbone (and, for --use_rollout, the attention rollout) runs in torch; everything after the head projection --
+    permute, AdaptiveAvgPool2d(grid_size), per-patch / per-centre L2 normalisation [:271-278,:304-305] -- is the ingest
+    kernel (vr_bank_ingest), which writes the fp32 banks and the operand copy of the fused rerank kernel batch by batch.
+    n_total (= len(dataset)) lets the banks be allocated up front; without it the batches are staged and ingested at the end.
+    Returns (patches [N,C,R], centers [N,C], rollout [N,R] or None, labels [N]) -- the engine's registered banks."""
     device = device or torch.device('cuda')
+    eng = RerankEngine.get(device)
     no_training = not training
     resize = None
-    if no_training:
-        if 7 % grid_size == 0:
-            resize = nn.AdaptiveAvgPool2d(grid_size)
-        else:
-            resize = nn.Sequential(nn.Upsample(grid_size * 4, mode='bilinear', align_corners=True),
-                                   nn.AdaptiveAvgPool2d(grid_size))
-    banks, centers, labels, rollouts = [], [], [], []
+    if no_training and 7 % grid_size != 0:   # [:228-234] the bilinear path stays in torch, the kernel then only normalises
+        resize = nn.Sequential(nn.Upsample(grid_size * 4, mode='bilinear', align_corners=True),
+                               nn.AdaptiveAvgPool2d(grid_size))
+    labels, staged = [], []
+    state = {"ready": False, "lo": 0}
+
+    def put(tokens, craw, roll, channel_major):
+        if not state["ready"]:
+            if n_total is None:
+                staged.append((tokens, craw, roll, channel_major))
+                return
+            c = tokens.shape[1] if channel_major else tokens.shape[2]
+            eng.new_bank(int(n_total), int(c), grid_size, with_rollout=use_rollout)
+            state["ready"] = True
+        lo = state["lo"]
+        eng.ingest(tokens, craw, lo, channel_major=channel_major)
+        if roll is not None:
+            eng.bank["rollout"][lo:lo + tokens.shape[0]].copy_(roll)
+        state["lo"] = lo + tokens.shape[0]
+
     with torch.no_grad():
         for inp in tqdm(dataloader, desc='Embedding Data...'):
             img, target = inp[1].to(device), inp[0]
             out = model(img)
+            roll = None
             if use_rollout:
                 rollout = get_attention_rollout(model.model, img, display_map=False)
-                rollouts.append(rollout[-1].mean(1).detach().to(device))
+                roll = rollout[-1].mean(1).detach().to(device).float()
             aux = None
             if isinstance(out, tuple):
                 out, aux = out
             if no_training:
                 _, tokens = aux
-                tokens = model.model.head(tokens).permute(0, 2, 1)           # bs x C x L
-                side = int(tokens.size(-1) ** 0.5)
-                tokens = tokens.reshape(tokens.size(0), -1, side, side)
-                if tokens.size(-1) != grid_size:
-                    tokens = resize(tokens)
-                banks.append(tokens.reshape(tokens.size(0), tokens.size(1), -1).detach())
-                centers.append(out.detach())
+                tokens = model.model.head(tokens)                            # bs x L x C  [:269]
+                side = int(tokens.size(1) ** 0.5)
+                if resize is not None and side != grid_size:
+                    t = tokens.permute(0, 2, 1).reshape(tokens.size(0), -1, side, side)
+                    put(resize(t).reshape(t.size(0), t.size(1), -1).detach().float(), out.detach().float(), roll, True)
+                else:
+                    put(tokens.detach().float(), out.detach().float(), roll, False)
             else:
-                banks.append(out.reshape(out.size(0), out.size(1), -1).detach())
-                centers.append(aux[0].detach())
+                put(out.reshape(out.size(0), out.size(1), -1).detach().float(), aux[0].detach().float(), roll, True)   # [:286-289]
             labels.append(torch.as_tensor(target).reshape(-1))
-    bank = torch.nn.functional.normalize(torch.cat(banks, 0).float(), p=2, dim=1)      # [:304]
-    center = torch.nn.functional.normalize(torch.cat(centers, 0).float(), p=2, dim=1)  # [:305]
-    roll = torch.cat(rollouts, 0).float() if use_rollout else None
-    return bank.contiguous(), center.contiguous(), roll, torch.cat(labels, 0).long()
+    labels = torch.cat(labels, 0).long()
+    if not state["ready"]:
+        n_total = int(labels.numel())
+        for item in staged:
+            put(*item)
+    assert state["lo"] == eng.bank["n"], f"embedded {state['lo']} images into banks sized for {eng.bank['n']}"
+    eng.register_labels(labels)
+    b = eng.bank
+    return b["patches"], b["centers"], b["rollout"], b["labels"]
 
 
 def evaluate_banks(patches, centers, rollout, labels, trunc_nums=None, use_uniform=False, use_inverse=False,
                    temperature=1.0, use_cls_token=False, ot_part=0.1, use_minus=False, use_rollout=False,
-                   device=None, return_extra=False):
+                   device=None, return_extra=False, use_soft=False):
     """PHASE B [:308-372,:402-416] over pre-built banks: the reference's query loop as one batched
     GPU pass.  Returns the reference's dict (percentages over the N gallery images)."""
     trunc_nums = trunc_nums or [0, 5, 10, 50, 100, 500, 1000]                   # [:309]
     if use_rollout and rollout is None and not use_uniform:
         raise ValueError("use_rollout needs the rollout bank")
     eng = RerankEngine.get(device if device is not None else (patches.device if patches.is_cuda else None))
-    eng.register(patches, centers, rollout, labels)
+    b = eng._bank
+    if b is not None and b["patches"] is patches and b["centers"] is centers and b["rollout"] is rollout:
+        # the banks embed_banks just ingested: already registered, operand copy written by the ingest kernel
+        if b["labels"] is not labels:
+            eng.register_labels(labels)
+    else:
+        eng.register(patches, centers, rollout, labels)
     params = OTParams.from_flags(use_rollout=use_rollout, use_uniform=use_uniform, use_inverse=use_inverse,
-                                 use_minus=use_minus, temperature=temperature, use_cls_token=use_cls_token,
-                                 ot_part=ot_part, ot_temp=0.05)                  # [:341], diml.py:325
+                                 use_minus=use_minus, use_soft=use_soft, temperature=temperature,
+                                 use_cls_token=use_cls_token, ot_part=ot_part, ot_temp=0.05)   # [:341], diml.py:325
     n = patches.shape[0]
     tallies, niter = vdist.evaluate_sharded(eng, trunc_nums, params)
     scale = float(n / 100)                                                       # [:403-405]
@@ -186,8 +216,9 @@ def evaluate(model, dataset, dataloader, training=False, trunc_nums=None, use_un
         if banks[3] is None or (use_rollout and not use_uniform and banks[2] is None):
             banks = None    # written by a run without labels / rollout: embed again
     if banks is None:
+        n_total = len(dataset) if hasattr(dataset, "__len__") else None
         banks = embed_banks(model, dataloader, training=training, grid_size=grid_size, use_rollout=use_rollout,
-                            device=device)
+                            device=device, n_total=n_total)
         if bank_cache:
             from vitrerank import bankfile
             bankfile.save(bank_cache, *banks)

@@ -96,6 +96,9 @@ def _stage1_off_path(name):
 
 def calc_distance(anchor, anchor_center, fb, fb_center, stage, use_uniform=False, use_exp=True, temperature=1.0,
                   use_cls_token=False):
+    if stage == 0:   # utilities/diml.py:150-153: a one-line torch expression, kept as such (off the rerank path)
+        dist = torch.sqrt(torch.sum(torch.pow(anchor_center - fb_center, 2), dim=1) + 1e-6).view(fb_center.size(0))
+        return dist, None
     _stage1_off_path("calc_distance")
 
 

@@ -41,14 +41,18 @@ def _load():
         "vr_device_info": (C.c_int, [vp, P(i32), P(i32)]),
         "vr_bank_register": (C.c_int, [vp, vp, vp, vp, vp, vp, i64, i32, i32]),
         "vr_bank_prepare": (C.c_int, [vp, i64, i64, vp]),
+        "vr_bank_labels": (C.c_int, [vp, vp, vp]),
+        "vr_bank_ingest": (C.c_int, [vp, vp, vp, i32, i64, i64, i32, i32, vp]),
         "vr_num_pos": (C.c_int, [vp, vp, i64, vp, P(i32), vp]),
         "vr_stage0_workspace_bytes": (sz, [vp, i64, i32]),
         "vr_stage0_topk": (C.c_int, [vp, vp, vp, i64, i64, i64, i32, vp, vp, vp, sz, vp]),
         "vr_stage0_stats": (C.c_int, [vp, P(C.c_uint32), vp]),
         "vr_rerank_workspace_bytes": (sz, [vp, i64, i32, P(OTParamsStruct)]),
         "vr_rerank_scores": (C.c_int, [vp, i64, i64, i64, i32, vp, i32, P(OTParamsStruct), vp, vp, vp, sz, vp]),
+        "vr_rerank_scores_queries": (C.c_int, [vp, vp, vp, vp, i64, i32, vp, i32, P(OTParamsStruct), vp, vp, vp, sz, vp]),
         "vr_finalize_workspace_bytes": (sz, [vp, i64, i32]),
         "vr_finalize": (C.c_int, [vp, i64, i64, i64, i32, i32, vp, vp, vp, P(i32), i32, vp, vp, vp, sz, vp]),
+        "vr_blend_rank": (C.c_int, [vp, i64, i32, i32, vp, vp, vp, vp, vp]),
         "vr_sinkhorn_workspace_bytes": (sz, [i64, i32, i32]),
         "vr_sinkhorn": (C.c_int, [vp, vp, vp, i64, i32, i32, i32, f32, vp, vp, vp, sz, vp]),
         "vr_calc_similarity_workspace_bytes": (sz, [i64, i32, i32, P(OTParamsStruct)]),

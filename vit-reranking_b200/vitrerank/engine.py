@@ -173,6 +173,44 @@ class RerankEngine:
         sp = C.c_void_p(stream.cuda_stream) if stream is not None else _stream(self.device)
         check(lib.vr_bank_prepare(self._h, first, count, sp), "vr_bank_prepare")
 
+    def new_bank(self, n, c, grid, with_rollout=False):
+        """Allocate and register empty banks for n images (patches [n, c, grid*grid], centres [n, c], rollout [n, grid*grid]):
+        the destination of ingest().  Labels are attached later with register_labels()."""
+        dev = self.device
+        r = grid * grid
+        patches = torch.empty(n, c, r, dtype=torch.float32, device=dev)
+        centers = torch.empty(n, c, dtype=torch.float32, device=dev)
+        rollout = torch.empty(n, r, dtype=torch.float32, device=dev) if with_rollout else None
+        check(lib.vr_bank_register(self._h, _ptr(patches), _ptr(centers), _ptr(rollout), _ptr(None), _ptr(None), n, c, r),
+              "vr_bank_register")
+        self._bank = dict(patches=patches, centers=centers, rollout=rollout, labels=None, num_pos=None, n=n, c=c, r=r,
+                          max_num_pos=1)
+        return self
+
+    def ingest(self, tokens, centers_raw, first, h=None, w=None, channel_major=False):
+        """One batch of backbone outputs into rows [first, first + B) of the registered banks (vr_bank_ingest): tokens
+        [B, L, C] (the head projection's output; channel_major: [B, C, L]), centers_raw [B, C] (or None).  Pools the h x w token
+        map to the bank's grid, normalises per patch / per centre and writes the operand copy of the fused kernel."""
+        b = self.bank
+        tokens = _f32(tokens, self.device)
+        centers_raw = _f32(centers_raw, self.device)
+        cnt = tokens.shape[0]
+        L = tokens.shape[2] if channel_major else tokens.shape[1]
+        if h is None:
+            h = w = int(round(L ** 0.5))
+        assert h * w == L and (tokens.shape[1] if channel_major else tokens.shape[2]) == b["c"]
+        check(lib.vr_bank_ingest(self._h, _ptr(tokens), _ptr(centers_raw), int(channel_major), first, cnt, h, w,
+                                 _stream(self.device)), "vr_bank_ingest")
+
+    def register_labels(self, labels):
+        """Attach labels (and their class counts) to banks filled by ingest(); the operand copy is kept."""
+        b = self.bank
+        labels = labels.to(device=self.device, dtype=torch.int64).contiguous()
+        num_pos, max_np = self.num_pos(labels)
+        check(lib.vr_bank_labels(self._h, _ptr(labels), _ptr(num_pos)), "vr_bank_labels")
+        b.update(labels=labels, num_pos=num_pos, max_num_pos=max_np)
+        return self
+
     @property
     def bank(self):
         if self._bank is None:
@@ -225,6 +263,23 @@ class RerankEngine:
               "vr_rerank_scores")
         return score, niter
 
+    def rerank_scores_queries(self, q_patches, q_centers, cand_idx, k, params: OTParams, q_rollout=None):
+        """rerank_scores for queries that are not gallery items (training_tools/val.py:159-190): q_patches [nq, C, R],
+        q_centers [nq, C]; candidates from the registered bank."""
+        q_patches, q_centers, q_rollout = _f32(q_patches, self.device), _f32(q_centers, self.device), _f32(q_rollout, self.device)
+        cand_idx = cand_idx.to(device=self.device, dtype=torch.int32).contiguous()
+        nq, stride = cand_idx.shape
+        assert q_patches.shape[0] == nq
+        ps = params.struct()
+        score = torch.empty(nq, k, dtype=torch.float32, device=self.device)
+        niter = torch.zeros(nq, dtype=torch.int32, device=self.device)
+        nb = lib.vr_rerank_workspace_bytes(self._h, nq, k, C.byref(ps))
+        ws = self._workspace("s1", nb)
+        check(lib.vr_rerank_scores_queries(self._h, _ptr(q_patches), _ptr(q_centers), _ptr(q_rollout), nq, k, _ptr(cand_idx),
+                                           stride, C.byref(ps), _ptr(score), _ptr(niter), _ptr(ws), ws.numel(),
+                                           _stream(self.device)), "vr_rerank_scores_queries")
+        return score, niter
+
     # ---- S5b ---------------------------------------------------------------------------------
     def finalize(self, approx_idx, approx_score, ot_score, k, trunc_nums, q_start=0, q_stride=1, tallies=None,
                  want_rank=False, want_per_query=False):
@@ -245,6 +300,14 @@ class RerankEngine:
             pq = ws[:nq * nt * 8 * 8].view(torch.float64).view(nq, nt, 8).clone()
             return tallies, rank, pq
         return tallies, rank
+
+    def blend_rank(self, approx_idx, approx_score, ot_score, k):
+        """approx_idx[q, argsort(ot_score[q] + approx_score[q, :k], descending)] (vr_blend_rank): [nq, k] int32."""
+        nq, kp = approx_idx.shape
+        rank = torch.empty(nq, k, dtype=torch.int32, device=self.device)
+        check(lib.vr_blend_rank(self._h, nq, k, kp, _ptr(approx_idx), _ptr(approx_score), _ptr(ot_score), _ptr(rank),
+                                _stream(self.device)), "vr_blend_rank")
+        return rank
 
     # ---- whole pass over the registered (device-resident) gallery ---------------------------------
     def evaluate(self, trunc_nums, params: OTParams, q_start=0, q_stride=1, nq=None, want_niter=False):
