@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(GP_THREADS) generic_prepare_kernel(GenArgs a) 
 
     // ---- sim[s][m] = sum_c F[c][s] * A[c][m], K = exp(-(1 - sim) / ot_temp) ----
     const int tx = tid & 15, ty = tid >> 4;
-    for (int s0 = 0; s0 < R; s0 += GP_T) {
+    for (int s0 = 0; s0 < (a.sim_done ? 0 : R); s0 += GP_T) {   // (tensor-core S3 already wrote sim and K: generic_s3.cu)
         for (int m0 = 0; m0 < R; m0 += GP_T) {
             float acc[4][4];
 #pragma unroll
@@ -479,6 +479,12 @@ int generic_rerank(GenArgs a, void* ws, size_t ws_bytes, cudaStream_t st) {
     }
     a.sim = w.sim; a.K = w.K; a.u = w.u; a.v = w.v; a.rv = w.rv; a.cv = w.cv; a.e = w.e;
     a.done = w.done; a.niter = w.niter;
+    a.sim_done = 0;
+    if (generic_sim_mma_supported(a.c, a.r)) {   // S3 on the tensor cores (C % 16 == 0, R <= 256)
+        int rc = generic_sim_mma(a, re, st);
+        if (rc) return rc;
+        a.sim_done = 1;
+    }
     size_t smem = (size_t)(2 * GP_KC * GP_T + 32 + 2 * a.c + 2 * a.r) * 4;
     if (smem > 48 * 1024)
         VR_CHECK_CUDA(cudaFuncSetAttribute(generic_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

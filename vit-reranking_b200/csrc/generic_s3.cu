@@ -1,0 +1,236 @@
+// S3 for the shape-generic path on the tensor cores: sim[s][m] = sum_c F[c][s] * A[c][m] (utilities/diml.py:100) and the Gibbs
+// kernel K = exp(-(1 - sim) / ot_temp) (:101-102) of every query / candidate pair, for any C % 16 == 0 and R <= 256 -- the
+// ViT-B/16 shape of BASELINE.json configs[4] (C = 768, R = 196: 59 Mflop per pair) in particular.  It replaces the scalar fp32
+// tile loop of generic_prepare_kernel, which spent ~85 % of a ViT-B/16 pass there.
+//
+// One CTA per pair, the recipe of pair_fused.cu's converter path at a larger scale: per 16-channel chunk the eight warps load
+// the candidate's and the query's rows (coalesced along the patches), split them as 64 x = hi + lo in fp16 and store the
+// K-major core-matrix operand tiles (A: up to 2 M-tiles of 128 candidate patches, B: the query patches padded to a multiple
+// of 16); warp 7 / lane 0 issues 3 tcgen05.mma per M-tile (lo.hi + hi.lo + hi.hi, fp32 accumulation in tensor memory) and commits;
+// two operand stages, `ready` / `mma_done` mbarriers hand them back and forth, the loads of the next chunk are in flight while
+// this one is converted.  Read-out: every warp takes 32 accumulator rows, transposes 32-column pieces through a padded
+// shared-memory tile and writes sim and K with full 128-byte rows.  |sim - fp32 chain| ~ 3e-7 (tools/umma_test.cu).
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "umma.cuh"
+
+namespace vr {
+
+constexpr int G3_THREADS = 256;
+constexpr float G3_SCALE = 64.0f;
+
+struct G3Args {
+    const float* q_patches;
+    const float* c_patches;
+    const int32_t* cand_idx;
+    int cand_stride;
+    int64_t q_start, q_stride;
+    int k, c, r, re, mt, rp16;
+    float ot_temp;
+    float* sim;   // [np, r, r]
+    float* K;     // [np, re, re]
+};
+
+__device__ __forceinline__ void g3_split(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const float y0 = x0 * G3_SCALE, y1 = x1 * G3_SCALE;
+    const __half2 h = __floats2half2_rn(y0, y1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(y0 - hf.x, y1 - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+__global__ void __launch_bounds__(G3_THREADS, 1) generic_sim_mma_kernel(G3Args a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t pair = blockIdx.x;
+    const int64_t qi = pair / a.k;
+    const int pi = (int)(pair % a.k);
+    const int64_t qid = a.q_start + qi * a.q_stride;
+    const int cand = a.cand_idx ? a.cand_idx[qi * a.cand_stride + pi] : pi;
+    if (cand < 0) return;   // padded shortlist entry: generic_prepare_kernel writes the zero problem
+    const int C = a.c, R = a.r, MT = a.mt, RP = a.rp16;
+    // operand stage: [A hi | A lo | B hi | B lo]; A plane = [kcore 2][row group MT*16][128 B], B plane = [kcore 2][RP/8][128 B]
+    const uint32_t planeA = (uint32_t)MT * 4096u, planeB = (uint32_t)RP * 32u;
+    const uint32_t stage_bytes = 2u * planeA + 2u * planeB;
+    unsigned char* stages = smem_raw;
+    float* tile = reinterpret_cast<float*>(smem_raw + 2 * stage_bytes) + warp * (32 * 33);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * stage_bytes + 8 * 32 * 33 * 4);
+    uint64_t* ready = bars;          // [2] operand stage stored by all warps
+    uint64_t* mma_done = bars + 2;   // [2] MMAs of the stage completed
+    uint64_t* s3_done = bars + 4;    // [1]
+    uint32_t* tmem_base = reinterpret_cast<uint32_t*>(bars + 5);
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; i++) {
+            mbar_init(ready + i, 8);
+            mbar_init(mma_done + i, 1);
+        }
+        mbar_init(s3_done, 1);
+        fence_mbar_init();
+    }
+    int ncols = 32;
+    while (ncols < MT * RP) ncols <<= 1;
+    if (warp == 0) tmem_alloc(tmem_base, (uint32_t)ncols);
+    // rows beyond R of both operands stay zero for the whole kernel
+    for (uint32_t e = tid; e < 2 * stage_bytes / 16; e += G3_THREADS) reinterpret_cast<uint4*>(stages)[e] = make_uint4(0u, 0u, 0u, 0u);
+    tmem_fence_before();
+    __syncthreads();
+    tmem_fence_after();
+    const uint32_t tmem0 = *tmem_base;
+
+    const float* Fg = a.c_patches + (int64_t)cand * C * R;
+    const float* Ag = a.q_patches + qid * (int64_t)C * R;
+    const int nitem = 2 * R;          // (kcore g, row s) items per operand; thread handles items tid and tid + 256
+    int it_s[2], it_g[2];
+    bool it_ok[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+        const int item = tid + G3_THREADS * u;
+        it_ok[u] = item < nitem;
+        it_g[u] = it_ok[u] ? item / R : 0;
+        it_s[u] = it_ok[u] ? item - it_g[u] * R : 0;
+    }
+    float xa[2][8], xb[2][8];
+    auto load_chunk = [&](int ch) {
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int64_t off = (int64_t)(ch * 16 + 8 * it_g[u]) * R + it_s[u];
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                xa[u][e] = it_ok[u] ? __ldg(Fg + off + (int64_t)e * R) : 0.f;
+                xb[u][e] = it_ok[u] ? __ldg(Ag + off + (int64_t)e * R) : 0.f;
+            }
+        }
+    };
+    const int NCH = C / 16;
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(RP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t st_addr = smem_u32(stages);
+    load_chunk(0);
+#pragma unroll 1
+    for (int ch = 0; ch < NCH; ch++) {
+        const int os = ch & 1;
+        uint32_t ah[2][4], al[2][4], bh[2][4], bl[2][4];
+#pragma unroll
+        for (int u = 0; u < 2; u++)
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                g3_split(xa[u][2 * w], xa[u][2 * w + 1], ah[u][w], al[u][w]);
+                g3_split(xb[u][2 * w], xb[u][2 * w + 1], bh[u][w], bl[u][w]);
+            }
+        if (ch + 1 < NCH) load_chunk(ch + 1);
+        if (ch > 1) mbar_wait(mma_done + os, ((ch >> 1) - 1) & 1);   // the stage is free once the MMAs of chunk ch - 2 are done
+        unsigned char* sg = stages + os * stage_bytes;
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            if (it_ok[u]) {
+                const int s = it_s[u], g = it_g[u];
+                const uint32_t offA = (uint32_t)g * (planeA / 2) + (uint32_t)(s >> 3) * 128u + (uint32_t)(s & 7) * 16u;
+                const uint32_t offB = (uint32_t)g * (planeB / 2) + (uint32_t)(s >> 3) * 128u + (uint32_t)(s & 7) * 16u;
+                *reinterpret_cast<uint4*>(sg + offA) = make_uint4(ah[u][0], ah[u][1], ah[u][2], ah[u][3]);
+                *reinterpret_cast<uint4*>(sg + planeA + offA) = make_uint4(al[u][0], al[u][1], al[u][2], al[u][3]);
+                *reinterpret_cast<uint4*>(sg + 2 * planeA + offB) = make_uint4(bh[u][0], bh[u][1], bh[u][2], bh[u][3]);
+                *reinterpret_cast<uint4*>(sg + 2 * planeA + planeB + offB) = make_uint4(bl[u][0], bl[u][1], bl[u][2], bl[u][3]);
+            }
+        }
+        fence_proxy_async();   // generic-proxy stores -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(ready + os));
+        if (warp == 7 && lane == 0) {
+            mbar_wait(ready + os, (ch >> 1) & 1);
+            tmem_fence_after();
+            const uint32_t base = st_addr + (uint32_t)os * stage_bytes;
+            const uint64_t bhd = umma_desc(base + 2 * planeA, planeB / 2, 128);
+            const uint64_t bld = umma_desc(base + 2 * planeA + planeB, planeB / 2, 128);
+            for (int t = 0; t < MT; t++) {
+                const uint64_t ahd = umma_desc(base + (uint32_t)t * 2048u, planeA / 2, 128);
+                const uint64_t ald = umma_desc(base + planeA + (uint32_t)t * 2048u, planeA / 2, 128);
+                const uint32_t d = tmem0 + (uint32_t)(t * RP);
+                umma_f16_i(d, ald, bhd, idesc, ch > 0 ? 1u : 0u);   // small terms first
+                umma_f16_i(d, ahd, bld, idesc, 1u);
+                umma_f16_i(d, ahd, bhd, idesc, 1u);
+            }
+            umma_commit(smem_u32(mma_done + os));
+            if (ch == NCH - 1) umma_commit(smem_u32(s3_done));
+        }
+        __syncwarp();
+    }
+    mbar_wait(s3_done, 0);
+    tmem_fence_after();
+
+    // ---- read-out: warp w owns accumulator rows 32 (w % 4) .. + 31 of M-tile w / 4 ----
+    const int t = warp >> 2;
+    if (t < MT) {
+        const int row0 = t * 128 + 32 * (warp & 3);
+        const uint32_t tl = tmem0 + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(t * RP);
+        float* simo = a.sim + pair * (int64_t)R * R;
+        float* Ko = a.K + pair * (int64_t)a.re * a.re;
+        constexpr float dscale = 1.0f / (G3_SCALE * G3_SCALE);
+        const float ot = a.ot_temp;
+        if (row0 < R) {
+            for (int c0 = 0; c0 < RP; c0 += 32) {
+                uint32_t v[32];
+                if (c0 + 32 <= RP) {
+                    tmem_ld32(tl + (uint32_t)c0, v);
+                } else {   // RP is a multiple of 16: a 16-column tail
+                    tmem_ld16(tl + (uint32_t)c0, v);
+#pragma unroll
+                    for (int i = 16; i < 32; i++) v[i] = 0u;
+                }
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; i++) tile[lane * 33 + i] = __uint_as_float(v[i]) * dscale;
+                __syncwarp();
+                const int m = c0 + lane;
+                for (int rr = 0; rr < 32; rr++) {
+                    const int s = row0 + rr;
+                    if (s < R && m < R) {
+                        const float x = tile[rr * 33 + lane];
+                        simo[(int64_t)s * R + m] = x;
+                        Ko[(int64_t)s * a.re + m] = expf(-(1.0f - x) / ot);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+    tmem_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem0, (uint32_t)ncols);
+}
+
+bool generic_sim_mma_supported(int c, int r) {
+    const char* e = getenv("VR_GENERIC_S3");   // VR_GENERIC_S3=fp32 keeps the scalar loop (A/B tests)
+    if (e && e[0] == 'f') return false;
+    return c >= 16 && c % 16 == 0 && r >= 8 && r <= 256;
+}
+
+int generic_sim_mma(const GenArgs& g, int re, cudaStream_t st) {
+    G3Args a{};
+    a.q_patches = g.q_patches;
+    a.c_patches = g.c_patches;
+    a.cand_idx = g.cand_idx;
+    a.cand_stride = g.cand_stride;
+    a.q_start = g.q_start;
+    a.q_stride = g.q_stride;
+    a.k = g.k;
+    a.c = g.c;
+    a.r = g.r;
+    a.re = re;
+    a.mt = (g.r + 127) / 128;
+    a.rp16 = (g.r + 15) / 16 * 16;
+    a.ot_temp = g.p.ot_temp;
+    a.sim = g.sim;
+    a.K = g.K;
+    const size_t stage = 2 * (size_t)a.mt * 4096 + 2 * (size_t)a.rp16 * 32;
+    const size_t smem = 2 * stage + 8 * 32 * 33 * 4 + 64;
+    VR_CHECK_CUDA(cudaFuncSetAttribute(generic_sim_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    generic_sim_mma_kernel<<<(unsigned)(g.nq * g.k), G3_THREADS, smem, st>>>(a);
+    VR_LAUNCH_CHECK();
+    return VR_OK;
+}
+
+}  // namespace vr

@@ -41,6 +41,7 @@ struct GenArgs {
     int k, c, r;
     vr_ot_params p;
     float part_bin;   // 1 - ot_part as the reference rounds it (set by generic_rerank)
+    int sim_done;     // sim and K were written by generic_sim_mma (tensor cores): generic_prepare_kernel skips its fp32 loop
     // workspace
     float* sim;    // [np, r, r]
     float* K;      // [np, re, re]
@@ -93,6 +94,10 @@ size_t generic_sinkhorn_workspace_bytes(int64_t b, int m, int n);
 int generic_rerank(GenArgs a, void* ws, size_t ws_bytes, cudaStream_t st);
 int generic_sinkhorn(const float* K, const float* u, const float* v, int64_t b, int m, int n, int max_iter,
                      float thresh, float* T, int32_t* niter, void* ws, size_t ws_bytes, cudaStream_t st);
+
+// generic_s3.cu
+bool generic_sim_mma_supported(int c, int r);
+int generic_sim_mma(const GenArgs& g, int re, cudaStream_t st);
 
 // finalize.cu
 size_t finalize_workspace_bytes(int64_t nq, int n_trunc);
