@@ -12,6 +12,8 @@
 // `done` flag, so no host synchronisation is needed.  Used for everything the fused
 // R=49/C=128/K<=104 kernel does not cover (K=1000 shortlists, 14x14 grids, C=768, the
 // direct Sinkhorn() call).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -443,12 +445,212 @@ size_t generic_rerank_workspace_bytes(int64_t nq, int k, int r, const vr_ot_para
 
 size_t generic_sinkhorn_workspace_bytes(int64_t b, int m, int n) { return carve(nullptr, 1, b, 0, m, n, false).bytes; }
 
+// ---- the whole loop in ONE launch: a CTA per pair keeps K in shared memory for all iterations ----
+// The multi-launch scheme above re-stages K (154 KB for a 14 x 14 grid) from global memory in every iteration and always issues
+// 2 x max_iter launches.  Here the k CTAs of a query stay resident and exchange their sum |dr| through tagged 8-byte words in
+// L2 (the protocol of pair_fused.cu's global transport: tag = (query + 1, iteration + 1), value = the float's bits; single-copy
+// atomic, no fence, the reader re-reads until every tag matches).  The sum of iteration t is published after its row pass and
+// looked at after the row pass of iteration t + 1, so its L2 round trip hides behind a column and a row pass; r and c are
+// double-buffered, so the state of iteration t is intact when its test fires.  Every CTA adds the k values in index order:
+// all reach the same decision.  Needs the k CTAs of a query co-resident (k <= SMs) and K in shared memory (rows <= ~236).
+constexpr int SKP_MAXK = 128;          // words per exchange step
+constexpr int SKP_SLOTS = 8;           // steps in flight (iteration & 7)
+constexpr int SKP_RING = 512;          // query slots of the exchange buffer (4 MB / (8 x 128 x 8 B))
+
+struct SkpArgs {
+    IterArgs it;
+    unsigned long long* part;
+    int max_iter;
+    float* dbg_err;
+};
+
+__global__ void __launch_bounds__(GI_THREADS, 1) generic_sk_persistent_kernel(SkpArgs p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const IterArgs& a = p.it;
+    const int rows = a.rows, cols = a.cols, ld = cols | 1;   // odd row stride: both passes are free of bank conflicts
+    const int rp = (rows + 3) & ~3, cp = (cols + 3) & ~3;
+    float* Ks = reinterpret_cast<float*>(smem_raw);   // [rows][ld]
+    float* cs = Ks + (size_t)rows * ld;               // [2][cp]
+    float* rs = cs + 2 * cp;                          // [2][rp]
+    float* us = rs + 2 * rp;                          // [rp]
+    float* vs = us + rp;                              // [cp]
+    float* red = vs + cp;                             // [32]
+    float* vals = red + 32;                           // [SKP_MAXK]
+    __shared__ int s_stop, s_first;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t pair = blockIdx.x;
+    const int64_t qi = pair / a.k;
+    const int pi = (int)(pair % a.k);
+    if (a.e[pair] < 0.f) return;                      // padded shortlist entry: not part of the problem
+    const float* Kg = a.K + pair * (int64_t)rows * cols;
+    for (int i = tid; i < rows * cols; i += GI_THREADS) Ks[(i / cols) * ld + (i % cols)] = Kg[i];
+    for (int s = tid; s < rows; s += GI_THREADS) {
+        us[s] = a.u[pair * rows + s];
+        rs[rp + s] = a.rv[pair * rows + s];           // "r of iteration -1" (ones, diml.py:43)
+    }
+    for (int m = tid; m < cols; m += GI_THREADS) {
+        vs[m] = a.v[pair * cols + m];
+        cs[cp + m] = a.cv[pair * cols + m];           // "c of iteration -1" (ones, diml.py:44)
+    }
+    // the members of this query that take part (padded entries carry e = -1), and the first of them (it reports)
+    if (warp == 0) {
+        int first = a.k;
+        for (int i = lane; i < a.k; i += 32) {
+            const bool act = a.e[qi * a.k + i] >= 0.f;
+            vals[i] = act ? 1.f : 0.f;
+            if (act) first = min(first, i);
+        }
+        first = __reduce_min_sync(0xffffffffu, first);
+        if (lane == 0) s_first = first;
+    }
+    __syncthreads();
+    const bool reporter = pi == s_first;
+    uint32_t actmask[SKP_MAXK / 32];
+#pragma unroll
+    for (int w = 0; w < SKP_MAXK / 32; w++) {
+        const int i = lane + 32 * w;
+        actmask[w] = (i < a.k && vals[i] != 0.f) ? 1u : 0u;   // this lane's members (lane + 32 w)
+    }
+    __syncthreads();
+    unsigned long long* part = p.part + (size_t)(qi & (SKP_RING - 1)) * (SKP_SLOTS * SKP_MAXK);
+    const uint32_t qtag = (uint32_t)(qi + 1) << 8;
+    const bool fused = (int64_t)rows * cols >= 400;   // torch.bmm's small-matrix path multiplies and adds unfused (see above)
+    const float denom = (float)a.k * (float)rows;
+    // warp 0: the batch mean of |dr| of iteration `step` (waits until every member has published it)
+    auto gather_mean = [&](int step) -> float {
+        const uint32_t want = qtag | (uint32_t)(step + 1);
+        const unsigned long long* src = part + (step & (SKP_SLOTS - 1)) * SKP_MAXK;
+        long long t0 = 0;
+#pragma unroll
+        for (int w = 0; w < SKP_MAXK / 32; w++) {
+            float v = 0.f;
+            if (actmask[w]) {
+                for (;;) {
+                    unsigned long long x;
+                    asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(x) : "l"(src + lane + 32 * w) : "memory");
+                    if ((uint32_t)(x >> 32) == want) {
+                        v = __uint_as_float((uint32_t)x);
+                        break;
+                    }
+                    if (t0 == 0) t0 = clock64();
+                    if (clock64() - t0 > 8000000000ll) __trap();   // ~4 s: the group is not co-resident; fail loudly
+                    __nanosleep(64);
+                }
+            }
+            vals[lane + 32 * w] = v;
+        }
+        __syncwarp();
+        float s = 0.f;
+        for (int i = 0; i < a.k; i++) s += vals[i];   // index order: identical in every CTA of the query
+        __syncwarp();
+        return s / denom;
+    };
+    int niter = p.max_iter, fin = (p.max_iter - 1) & 1;
+    if (p.max_iter == 0) fin = 1;
+    for (int it = 0; it < p.max_iter; it++) {
+        const int cur = it & 1, prv = cur ^ 1;
+        // row pass: r = u / (K c)
+        float e = 0.f;
+        for (int s = tid; s < rows; s += GI_THREADS) {
+            const float* Kr = Ks + (size_t)s * ld;
+            const float* c = cs + prv * cp;
+            float y = 0.f;
+            if (fused)
+                for (int m = 0; m < cols; m++) y = fmaf(Kr[m], c[m], y);
+            else
+                for (int m = 0; m < cols; m++) y = __fadd_rn(y, __fmul_rn(Kr[m], c[m]));
+            const float rn = us[s] / y;
+            e += fabsf(rn - rs[prv * rp + s]);
+            rs[cur * rp + s] = rn;
+        }
+        e = block_reduce_sum(e, red);                 // (includes the barrier that publishes r)
+        if (tid == 0) {
+            const unsigned long long w = ((unsigned long long)(qtag | (uint32_t)(it + 1)) << 32) | (unsigned long long)__float_as_uint(e);
+            asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(part + (it & (SKP_SLOTS - 1)) * SKP_MAXK + pi), "l"(w) : "memory");
+        }
+        if (it >= 1) {   // the test of iteration it - 1
+            if (warp == 0) {
+                const float mean = gather_mean(it - 1);
+                if (lane == 0) {
+                    if (reporter && p.dbg_err) p.dbg_err[qi * p.max_iter + it - 1] = mean;
+                    s_stop = mean < a.thresh ? 1 : 0;             // NaN: no stop, like `nan < thresh`
+                }
+            }
+            __syncthreads();
+            if (s_stop) {   // iteration it - 1 was the last one: its r and c are still in place
+                niter = it;
+                fin = prv;
+                break;
+            }
+        }
+        // column pass: c = v / (K^T r)
+        for (int m = tid; m < cols; m += GI_THREADS) {
+            const float* r = rs + cur * rp;
+            float x = 0.f;
+            if (fused)
+                for (int s = 0; s < rows; s++) x = fmaf(Ks[(size_t)s * ld + m], r[s], x);
+            else
+                for (int s = 0; s < rows; s++) x = __fadd_rn(x, __fmul_rn(Ks[(size_t)s * ld + m], r[s]));
+            cs[cur * cp + m] = vs[m] / x;
+        }
+        __syncthreads();
+    }
+    if (reporter && p.dbg_err && niter == p.max_iter && p.max_iter >= 1 && warp == 0) {
+        // the last iteration's value was not needed for a decision: report it for the trace all the same
+        const float mean = gather_mean(p.max_iter - 1);
+        if (lane == 0) p.dbg_err[qi * p.max_iter + p.max_iter - 1] = mean;
+    }
+    for (int s = tid; s < rows; s += GI_THREADS) a.rv[pair * rows + s] = rs[fin * rp + s];
+    for (int m = tid; m < cols; m += GI_THREADS) a.cv[pair * cols + m] = cs[fin * cp + m];
+    if (reporter && tid == 0) a.niter[qi] = niter;
+}
+
+static size_t skp_smem(int rows, int cols) {
+    const int ld = cols | 1, rp = (rows + 3) & ~3, cp = (cols + 3) & ~3;
+    return ((size_t)rows * ld + 3 * (size_t)cp + 3 * (size_t)rp + 32 + SKP_MAXK) * 4;
+}
+
+// The persistent kernel applies when K fits in shared memory, a query has at most 128 members that can all be resident, and
+// the iteration / query counts fit the tag.  VR_GENERIC_SK=launches keeps the multi-launch scheme (A/B tests).
+static bool skp_usable(const IterArgs& it, int64_t nq, int max_iter, int* resident_out) {
+    const char* e = getenv("VR_GENERIC_SK");
+    if (e && e[0] == 'l') return false;
+    const size_t smem = skp_smem(it.rows, it.cols);
+    if (smem > 225 * 1024 || it.k > SKP_MAXK || max_iter > 254 || max_iter < 1 || nq >= (1ll << 23)) return false;
+    if (cudaFuncSetAttribute(generic_sk_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
+    int dev = 0, sms = 0, per_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, generic_sk_persistent_kernel, GI_THREADS, smem) != cudaSuccess)
+        return false;
+    *resident_out = per_sm * sms;
+    return per_sm * sms >= it.k;   // the members of a query wait for one another: all must fit on the device
+}
+
 static int run_iterations(const IterArgs& it, int64_t nq, int64_t np, int max_iter, float* dbg_err, cudaStream_t st) {
     const size_t base = (size_t)(it.rows + it.cols + 32) * 4;
     const size_t staged = base + (size_t)it.rows * (it.cols + 1) * 4;
     const bool use_staged = staged <= 200 * 1024;
     const size_t smem = use_staged ? staged : base;
     VR_REQUIRE(base <= 48 * 1024, "sinkhorn: %d x %d too large", it.rows, it.cols);
+    int resident = 0;
+    if (skp_usable(it, nq, max_iter, &resident)) {
+        SkpArgs p{it, nullptr, max_iter, dbg_err};
+        size_t xbytes = 0;
+        int rc = pair_exchange_begin(st, &p.part, &xbytes);
+        if (rc) return rc;
+        if (xbytes >= (size_t)SKP_RING * SKP_SLOTS * SKP_MAXK * 8) {
+            generic_sk_persistent_kernel<<<(unsigned)np, GI_THREADS, skp_smem(it.rows, it.cols), st>>>(p);
+            const cudaError_t le = cudaGetLastError();
+            vr::g_launches++;
+            rc = pair_exchange_end(st);
+            if (le != cudaSuccess) {
+                set_error("generic_sk_persistent_kernel: %s", cudaGetErrorString(le));
+                return VR_E_CUDA;
+            }
+            return rc;
+        }
+        if ((rc = pair_exchange_end(st))) return rc;
+    }
     if (use_staged && smem > 48 * 1024)
         VR_CHECK_CUDA(cudaFuncSetAttribute(generic_iter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem));

@@ -81,6 +81,8 @@ bool pair_fused_supports(int c, int r, int k, const vr_ot_params* p, bool scores
 float partial_ot_bin(float ot_part);   // 1 - ot_part rounded as diml.py:61 rounds it
 bool pair_fused_supports_wide(int c, int r, int k, const vr_ot_params* p);   // 112 < k <= 1024, scores only
 int pair_fused_launch(const PairArgs& a, int64_t nq, cudaStream_t st);
+int pair_exchange_begin(cudaStream_t st, unsigned long long** part, size_t* bytes);   // exchange buffer + launch serialisation
+int pair_exchange_end(cudaStream_t st);
 int pair_fused_ctx_open(int device);    // vr_create / vr_destroy: the last context on a device frees the exchange buffer
 void pair_fused_ctx_close(int device);
 size_t pair_fused_packed_bytes(int64_t n);   // both roles
