@@ -453,6 +453,11 @@ size_t generic_sinkhorn_workspace_bytes(int64_t b, int m, int n) { return carve(
 // looked at after the row pass of iteration t + 1, so its L2 round trip hides behind a column and a row pass; r and c are
 // double-buffered, so the state of iteration t is intact when its test fires.  Every CTA adds the k values in index order:
 // all reach the same decision.  Needs the k CTAs of a query co-resident (k <= SMs) and K in shared memory (rows <= ~236).
+__host__ __device__ inline int skp_ld(int cols) {
+    int q = (cols + 3) / 4;
+    if ((q & 1) == 0) q++;
+    return 4 * q;
+}
 constexpr int SKP_MAXK = 128;          // words per exchange step
 constexpr int SKP_SLOTS = 8;           // steps in flight (iteration & 7)
 constexpr int SKP_RING = 512;          // query slots of the exchange buffer (4 MB / (8 x 128 x 8 B))
@@ -467,7 +472,9 @@ struct SkpArgs {
 __global__ void __launch_bounds__(GI_THREADS, 1) generic_sk_persistent_kernel(SkpArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const IterArgs& a = p.it;
-    const int rows = a.rows, cols = a.cols, ld = cols | 1;   // odd row stride: both passes are free of bank conflicts
+    // row stride: a multiple of 4 floats with ld / 4 odd -- the row pass reads K with LDS.128 (lane = row: the 8 lanes of a
+    // quarter-warp fall on 8 distinct 4-bank groups), the column pass with LDS.32 (lane = column: consecutive words)
+    const int rows = a.rows, cols = a.cols, ld = skp_ld(cols);
     const int rp = (rows + 3) & ~3, cp = (cols + 3) & ~3;
     float* Ks = reinterpret_cast<float*>(smem_raw);   // [rows][ld]
     float* cs = Ks + (size_t)rows * ld;               // [2][cp]
@@ -477,20 +484,38 @@ __global__ void __launch_bounds__(GI_THREADS, 1) generic_sk_persistent_kernel(Sk
     float* red = vs + cp;                             // [32]
     float* vals = red + 32;                           // [SKP_MAXK]
     __shared__ int s_stop, s_first;
+    __shared__ __align__(8) uint64_t kbar;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t pair = blockIdx.x;
     const int64_t qi = pair / a.k;
     const int pi = (int)(pair % a.k);
     if (a.e[pair] < 0.f) return;                      // padded shortlist entry: not part of the problem
     const float* Kg = a.K + pair * (int64_t)rows * cols;
-    for (int i = tid; i < rows * cols; i += GI_THREADS) Ks[(i / cols) * ld + (i % cols)] = Kg[i];
+    // K -> shared memory once: one bulk copy when the rows need no padding (cols = ld, e.g. 196) and the matrix is 16-byte aligned,
+    // else row by row through registers with a few loads in flight per thread
+    const bool bulk = ld == cols && ((reinterpret_cast<uintptr_t>(Kg) & 15) == 0) && ((size_t)rows * cols * 4 < (1u << 20));
+    if (bulk) {
+        if (tid == 0) {
+            mbar_init(&kbar, 1);
+            fence_mbar_init();
+            mbar_expect_tx(&kbar, (uint32_t)(rows * cols * 4));
+            bulk_g2s(Ks, Kg, (uint32_t)(rows * cols * 4), &kbar);
+        }
+    } else {
+        for (int s = warp; s < rows; s += GI_THREADS / 32) {
+            float* dst = Ks + (size_t)s * ld;
+            const float* src = Kg + (int64_t)s * cols;
+            for (int m = lane; m < ld; m += 32) dst[m] = m < cols ? __ldg(src + m) : 0.f;
+        }
+    }
     for (int s = tid; s < rows; s += GI_THREADS) {
         us[s] = a.u[pair * rows + s];
         rs[rp + s] = a.rv[pair * rows + s];           // "r of iteration -1" (ones, diml.py:43)
     }
-    for (int m = tid; m < cols; m += GI_THREADS) {
-        vs[m] = a.v[pair * cols + m];
-        cs[cp + m] = a.cv[pair * cols + m];           // "c of iteration -1" (ones, diml.py:44)
+    for (int m = tid; m < cp; m += GI_THREADS) {
+        vs[m] = m < cols ? a.v[pair * cols + m] : 0.f;
+        cs[cp + m] = m < cols ? a.cv[pair * cols + m] : 0.f;   // "c of iteration -1" (ones, diml.py:44); padding stays 0
+        cs[m] = 0.f;
     }
     // the members of this query that take part (padded entries carry e = -1), and the first of them (it reports)
     if (warp == 0) {
@@ -504,6 +529,7 @@ __global__ void __launch_bounds__(GI_THREADS, 1) generic_sk_persistent_kernel(Sk
         if (lane == 0) s_first = first;
     }
     __syncthreads();
+    if (bulk) mbar_wait(&kbar, 0);
     const bool reporter = pi == s_first;
     uint32_t actmask[SKP_MAXK / 32];
 #pragma unroll
@@ -552,13 +578,23 @@ __global__ void __launch_bounds__(GI_THREADS, 1) generic_sk_persistent_kernel(Sk
         // row pass: r = u / (K c)
         float e = 0.f;
         for (int s = tid; s < rows; s += GI_THREADS) {
-            const float* Kr = Ks + (size_t)s * ld;
-            const float* c = cs + prv * cp;
+            const float4* Kr = reinterpret_cast<const float4*>(Ks + (size_t)s * ld);
+            const float4* c = reinterpret_cast<const float4*>(cs + prv * cp);
             float y = 0.f;
-            if (fused)
-                for (int m = 0; m < cols; m++) y = fmaf(Kr[m], c[m], y);
-            else
-                for (int m = 0; m < cols; m++) y = __fadd_rn(y, __fmul_rn(Kr[m], c[m]));
+            if (fused) {   // (padding columns: K = 0 and c = 0 add exact zeros at the end of the chain)
+#pragma unroll 4
+                for (int m4 = 0; m4 < cp / 4; m4++) {
+                    const float4 kv = Kr[m4], cv = c[m4];
+                    y = fmaf(kv.x, cv.x, y);
+                    y = fmaf(kv.y, cv.y, y);
+                    y = fmaf(kv.z, cv.z, y);
+                    y = fmaf(kv.w, cv.w, y);
+                }
+            } else {
+                const float* K1 = Ks + (size_t)s * ld;
+                const float* c1 = cs + prv * cp;
+                for (int m = 0; m < cols; m++) y = __fadd_rn(y, __fmul_rn(K1[m], c1[m]));
+            }
             const float rn = us[s] / y;
             e += fabsf(rn - rs[prv * rp + s]);
             rs[cur * rp + s] = rn;
@@ -606,7 +642,7 @@ __global__ void __launch_bounds__(GI_THREADS, 1) generic_sk_persistent_kernel(Sk
 }
 
 static size_t skp_smem(int rows, int cols) {
-    const int ld = cols | 1, rp = (rows + 3) & ~3, cp = (cols + 3) & ~3;
+    const int ld = skp_ld(cols), rp = (rows + 3) & ~3, cp = (cols + 3) & ~3;
     return ((size_t)rows * ld + 3 * (size_t)cp + 3 * (size_t)rp + 32 + SKP_MAXK) * 4;
 }
 

@@ -19,8 +19,10 @@
 
 namespace vr {
 
-constexpr int G3_THREADS = 256;
+constexpr int G3_THREADS = 512;
+constexpr int G3_CONV_WARPS = 14;   // warps 0..13 convert (one (row, channel octet) item per thread), 14 = TMA producer, 15 = MMA issuer
 constexpr float G3_SCALE = 64.0f;
+constexpr int G3_NS = 4;   // raw-row staging ring (TMA): chunks in flight ahead of the converters
 
 struct G3Args {
     const float* q_patches;
@@ -43,6 +45,11 @@ __device__ __forceinline__ void g3_split(float x0, float x1, uint32_t& hi, uint3
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+// TMA = true (R % 4 == 0, 16-byte aligned banks): the 16 channel rows of a chunk are contiguous in both banks (12.5 KB at
+// R = 196), so one thread fetches them with two cp.async.bulk per chunk into a 4-deep staging ring, three chunks ahead of the
+// converters -- register loads one chunk ahead left the CTA (one per SM: its accumulators take 416 of the 512 TMEM columns)
+// waiting a full HBM latency per chunk (83 us per pair; 2.1 TB/s over the GPU).
+template <bool TMA>
 __global__ void __launch_bounds__(G3_THREADS, 1) generic_sim_mma_kernel(G3Args a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -58,18 +65,26 @@ __global__ void __launch_bounds__(G3_THREADS, 1) generic_sim_mma_kernel(G3Args a
     const uint32_t stage_bytes = 2u * planeA + 2u * planeB;
     unsigned char* stages = smem_raw;
     float* tile = reinterpret_cast<float*>(smem_raw + 2 * stage_bytes) + warp * (32 * 33);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * stage_bytes + 8 * 32 * 33 * 4);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * stage_bytes + 16 * 32 * 33 * 4);
     uint64_t* ready = bars;          // [2] operand stage stored by all warps
     uint64_t* mma_done = bars + 2;   // [2] MMAs of the stage completed
     uint64_t* s3_done = bars + 4;    // [1]
-    uint32_t* tmem_base = reinterpret_cast<uint32_t*>(bars + 5);
+    uint64_t* full = bars + 5;       // [NS] raw rows of a chunk have landed
+    uint64_t* empty = full + G3_NS;  // [NS] every warp has taken them into registers
+    uint32_t* tmem_base = reinterpret_cast<uint32_t*>(empty + G3_NS);
+    float* raw = reinterpret_cast<float*>(smem_raw + 2 * stage_bytes + 16 * 32 * 33 * 4 + 256);   // [NS][2][16 * R]
+    const uint32_t raw_half = (uint32_t)(16 * R) * 4u;
 
     if (tid == 0) {
         for (int i = 0; i < 2; i++) {
-            mbar_init(ready + i, 8);
+            mbar_init(ready + i, G3_CONV_WARPS);
             mbar_init(mma_done + i, 1);
         }
         mbar_init(s3_done, 1);
+        for (int i = 0; i < G3_NS; i++) {
+            mbar_init(full + i, 1);
+            mbar_init(empty + i, G3_CONV_WARPS);
+        }
         fence_mbar_init();
     }
     int ncols = 32;
@@ -84,85 +99,106 @@ __global__ void __launch_bounds__(G3_THREADS, 1) generic_sim_mma_kernel(G3Args a
 
     const float* Fg = a.c_patches + (int64_t)cand * C * R;
     const float* Ag = a.q_patches + qid * (int64_t)C * R;
-    const int nitem = 2 * R;          // (kcore g, row s) items per operand; thread handles items tid and tid + 256
-    int it_s[2], it_g[2];
-    bool it_ok[2];
-#pragma unroll
-    for (int u = 0; u < 2; u++) {
-        const int item = tid + G3_THREADS * u;
-        it_ok[u] = item < nitem;
-        it_g[u] = it_ok[u] ? item / R : 0;
-        it_s[u] = it_ok[u] ? item - it_g[u] * R : 0;
-    }
-    float xa[2][8], xb[2][8];
-    auto load_chunk = [&](int ch) {
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-            const int64_t off = (int64_t)(ch * 16 + 8 * it_g[u]) * R + it_s[u];
-#pragma unroll
-            for (int e = 0; e < 8; e++) {
-                xa[u][e] = it_ok[u] ? __ldg(Fg + off + (int64_t)e * R) : 0.f;
-                xb[u][e] = it_ok[u] ? __ldg(Ag + off + (int64_t)e * R) : 0.f;
-            }
-        }
-    };
+    // (kcore g, row s) items per operand: 2 R <= 448 = one per converter thread
+    const int nitem = 2 * R;
+    const bool conv = warp < G3_CONV_WARPS;
+    const bool it_ok = conv && tid < nitem;
+    const int it_g = it_ok ? tid / R : 0;
+    const int it_s = it_ok ? tid - it_g * R : 0;
     const int NCH = C / 16;
     const uint32_t idesc = (1u << 4) | ((uint32_t)(RP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t st_addr = smem_u32(stages);
-    load_chunk(0);
-#pragma unroll 1
-    for (int ch = 0; ch < NCH; ch++) {
-        const int os = ch & 1;
-        uint32_t ah[2][4], al[2][4], bh[2][4], bl[2][4];
+    if (warp == G3_CONV_WARPS) {
+        // ---- producer (TMA only): both banks' 16 rows of every chunk -> staging ring, NS - 1 chunks ahead of the converters ----
+        if (TMA && lane == 0) {
+            for (int ch = 0; ch < NCH; ch++) {
+                const int stg = ch % G3_NS;
+                if (ch >= G3_NS) mbar_wait(empty + stg, ((ch / G3_NS) - 1) & 1);
+                mbar_expect_tx(full + stg, 2 * raw_half);
+                bulk_g2s(raw + (size_t)stg * 2 * 16 * R, Fg + (int64_t)ch * 16 * R, raw_half, full + stg);
+                bulk_g2s(raw + (size_t)stg * 2 * 16 * R + 16 * R, Ag + (int64_t)ch * 16 * R, raw_half, full + stg);
+            }
+        }
+    } else if (warp == G3_CONV_WARPS + 1) {
+        // ---- MMA issuer ----
+        if (lane == 0) {
+            for (int ch = 0; ch < NCH; ch++) {
+                const int os = ch & 1;
+                mbar_wait(ready + os, (ch >> 1) & 1);
+                tmem_fence_after();
+                const uint32_t base = st_addr + (uint32_t)os * stage_bytes;
+                const uint64_t bhd = umma_desc(base + 2 * planeA, planeB / 2, 128);
+                const uint64_t bld = umma_desc(base + 2 * planeA + planeB, planeB / 2, 128);
+                for (int t = 0; t < MT; t++) {
+                    const uint64_t ahd = umma_desc(base + (uint32_t)t * 2048u, planeA / 2, 128);
+                    const uint64_t ald = umma_desc(base + planeA + (uint32_t)t * 2048u, planeA / 2, 128);
+                    const uint32_t d = tmem0 + (uint32_t)(t * RP);
+                    umma_f16_i(d, ald, bhd, idesc, ch > 0 ? 1u : 0u);   // small terms first
+                    umma_f16_i(d, ahd, bld, idesc, 1u);
+                    umma_f16_i(d, ahd, bhd, idesc, 1u);
+                }
+                umma_commit(smem_u32(mma_done + os));
+                if (ch == NCH - 1) umma_commit(smem_u32(s3_done));
+            }
+        }
+    } else {
+        // ---- converters ----
+        float xa[8], xb[8];
+        auto load_chunk = [&](int ch) {
+            if (TMA) {
+                const int stg = ch % G3_NS;
+                mbar_wait(full + stg, (ch / G3_NS) & 1);
+                const float* ra = raw + (size_t)stg * 2 * 16 * R;
+                const float* rb = ra + 16 * R;
+                const int off = 8 * it_g * R + it_s;
 #pragma unroll
-        for (int u = 0; u < 2; u++)
+                for (int e = 0; e < 8; e++) {
+                    xa[e] = it_ok ? ra[off + e * R] : 0.f;
+                    xb[e] = it_ok ? rb[off + e * R] : 0.f;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(empty + stg));
+                return;
+            }
+            const int64_t off = (int64_t)(ch * 16 + 8 * it_g) * R + it_s;
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                xa[e] = it_ok ? __ldg(Fg + off + (int64_t)e * R) : 0.f;
+                xb[e] = it_ok ? __ldg(Ag + off + (int64_t)e * R) : 0.f;
+            }
+        };
+        const uint32_t offA = (uint32_t)it_g * (planeA / 2) + (uint32_t)(it_s >> 3) * 128u + (uint32_t)(it_s & 7) * 16u;
+        const uint32_t offB = (uint32_t)it_g * (planeB / 2) + (uint32_t)(it_s >> 3) * 128u + (uint32_t)(it_s & 7) * 16u;
+        load_chunk(0);
+#pragma unroll 1
+        for (int ch = 0; ch < NCH; ch++) {
+            const int os = ch & 1;
+            uint32_t ah[4], al[4], bh[4], bl[4];
 #pragma unroll
             for (int w = 0; w < 4; w++) {
-                g3_split(xa[u][2 * w], xa[u][2 * w + 1], ah[u][w], al[u][w]);
-                g3_split(xb[u][2 * w], xb[u][2 * w + 1], bh[u][w], bl[u][w]);
+                g3_split(xa[2 * w], xa[2 * w + 1], ah[w], al[w]);
+                g3_split(xb[2 * w], xb[2 * w + 1], bh[w], bl[w]);
             }
-        if (ch + 1 < NCH) load_chunk(ch + 1);
-        if (ch > 1) mbar_wait(mma_done + os, ((ch >> 1) - 1) & 1);   // the stage is free once the MMAs of chunk ch - 2 are done
-        unsigned char* sg = stages + os * stage_bytes;
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-            if (it_ok[u]) {
-                const int s = it_s[u], g = it_g[u];
-                const uint32_t offA = (uint32_t)g * (planeA / 2) + (uint32_t)(s >> 3) * 128u + (uint32_t)(s & 7) * 16u;
-                const uint32_t offB = (uint32_t)g * (planeB / 2) + (uint32_t)(s >> 3) * 128u + (uint32_t)(s & 7) * 16u;
-                *reinterpret_cast<uint4*>(sg + offA) = make_uint4(ah[u][0], ah[u][1], ah[u][2], ah[u][3]);
-                *reinterpret_cast<uint4*>(sg + planeA + offA) = make_uint4(al[u][0], al[u][1], al[u][2], al[u][3]);
-                *reinterpret_cast<uint4*>(sg + 2 * planeA + offB) = make_uint4(bh[u][0], bh[u][1], bh[u][2], bh[u][3]);
-                *reinterpret_cast<uint4*>(sg + 2 * planeA + planeB + offB) = make_uint4(bl[u][0], bl[u][1], bl[u][2], bl[u][3]);
+            if (ch + 1 < NCH) load_chunk(ch + 1);
+            if (ch > 1) mbar_wait(mma_done + os, ((ch >> 1) - 1) & 1);   // the stage is free once the MMAs of chunk ch - 2 are done
+            unsigned char* sg = stages + os * stage_bytes;
+            if (it_ok) {
+                *reinterpret_cast<uint4*>(sg + offA) = make_uint4(ah[0], ah[1], ah[2], ah[3]);
+                *reinterpret_cast<uint4*>(sg + planeA + offA) = make_uint4(al[0], al[1], al[2], al[3]);
+                *reinterpret_cast<uint4*>(sg + 2 * planeA + offB) = make_uint4(bh[0], bh[1], bh[2], bh[3]);
+                *reinterpret_cast<uint4*>(sg + 2 * planeA + planeB + offB) = make_uint4(bl[0], bl[1], bl[2], bl[3]);
             }
+            fence_proxy_async();   // generic-proxy stores -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(ready + os));
         }
-        fence_proxy_async();   // generic-proxy stores -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(ready + os));
-        if (warp == 7 && lane == 0) {
-            mbar_wait(ready + os, (ch >> 1) & 1);
-            tmem_fence_after();
-            const uint32_t base = st_addr + (uint32_t)os * stage_bytes;
-            const uint64_t bhd = umma_desc(base + 2 * planeA, planeB / 2, 128);
-            const uint64_t bld = umma_desc(base + 2 * planeA + planeB, planeB / 2, 128);
-            for (int t = 0; t < MT; t++) {
-                const uint64_t ahd = umma_desc(base + (uint32_t)t * 2048u, planeA / 2, 128);
-                const uint64_t ald = umma_desc(base + planeA + (uint32_t)t * 2048u, planeA / 2, 128);
-                const uint32_t d = tmem0 + (uint32_t)(t * RP);
-                umma_f16_i(d, ald, bhd, idesc, ch > 0 ? 1u : 0u);   // small terms first
-                umma_f16_i(d, ahd, bld, idesc, 1u);
-                umma_f16_i(d, ahd, bhd, idesc, 1u);
-            }
-            umma_commit(smem_u32(mma_done + os));
-            if (ch == NCH - 1) umma_commit(smem_u32(s3_done));
-        }
-        __syncwarp();
     }
     mbar_wait(s3_done, 0);
     tmem_fence_after();
 
-    // ---- read-out: warp w owns accumulator rows 32 (w % 4) .. + 31 of M-tile w / 4 ----
-    const int t = warp >> 2;
+    // ---- read-out: warp w owns accumulator rows 32 (w % 4) .. + 31 of M-tile (w / 4) % 2 and column half w / 8 ----
+    const int t = (warp >> 2) & 1;
+    const int chalf = warp >> 3;
     if (t < MT) {
         const int row0 = t * 128 + 32 * (warp & 3);
         const uint32_t tl = tmem0 + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(t * RP);
@@ -171,7 +207,8 @@ __global__ void __launch_bounds__(G3_THREADS, 1) generic_sim_mma_kernel(G3Args a
         constexpr float dscale = 1.0f / (G3_SCALE * G3_SCALE);
         const float ot = a.ot_temp;
         if (row0 < R) {
-            for (int c0 = 0; c0 < RP; c0 += 32) {
+            const int cmid = ((RP / 32 + 1) / 2) * 32;   // columns [0, cmid) to half 0, [cmid, RP) to half 1
+            for (int c0 = chalf ? cmid : 0; c0 < (chalf ? RP : cmid); c0 += 32) {
                 uint32_t v[32];
                 if (c0 + 32 <= RP) {
                     tmem_ld32(tl + (uint32_t)c0, v);
@@ -205,7 +242,7 @@ __global__ void __launch_bounds__(G3_THREADS, 1) generic_sim_mma_kernel(G3Args a
 bool generic_sim_mma_supported(int c, int r) {
     const char* e = getenv("VR_GENERIC_S3");   // VR_GENERIC_S3=fp32 keeps the scalar loop (A/B tests)
     if (e && e[0] == 'f') return false;
-    return c >= 16 && c % 16 == 0 && r >= 8 && r <= 256;
+    return c >= 16 && c % 16 == 0 && r >= 8 && 2 * r <= G3_CONV_WARPS * 32;   // (one converter item per thread: R <= 224)
 }
 
 int generic_sim_mma(const GenArgs& g, int re, cudaStream_t st) {
@@ -226,9 +263,13 @@ int generic_sim_mma(const GenArgs& g, int re, cudaStream_t st) {
     a.sim = g.sim;
     a.K = g.K;
     const size_t stage = 2 * (size_t)a.mt * 4096 + 2 * (size_t)a.rp16 * 32;
-    const size_t smem = 2 * stage + 8 * 32 * 33 * 4 + 64;
-    VR_CHECK_CUDA(cudaFuncSetAttribute(generic_sim_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    generic_sim_mma_kernel<<<(unsigned)(g.nq * g.k), G3_THREADS, smem, st>>>(a);
+    const size_t raw = (size_t)G3_NS * 2 * 16 * g.r * 4;
+    const bool tma = g.r % 4 == 0 && ((uintptr_t)g.q_patches & 15) == 0 && ((uintptr_t)g.c_patches & 15) == 0 &&
+                     2 * stage + 16 * 32 * 33 * 4 + 256 + raw <= 225 * 1024;
+    const size_t smem = 2 * stage + 16 * 32 * 33 * 4 + 256 + (tma ? raw : 0);
+    auto* kern = tma ? generic_sim_mma_kernel<true> : generic_sim_mma_kernel<false>;
+    VR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)(g.nq * g.k), G3_THREADS, smem, st>>>(a);
     VR_LAUNCH_CHECK();
     return VR_OK;
 }
