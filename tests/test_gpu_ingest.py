@@ -44,7 +44,10 @@ def test_ingest_bit_exact(eng, n, c, side, grid):
         assert torch.equal(b["patches"].cpu(), ref_p), (b["patches"].cpu() - ref_p).abs().max()
     else:                                        # 3 x 3 blocks (no reference config pools that way): the mean's rounding may differ
         torch.testing.assert_close(b["patches"].cpu(), ref_p, rtol=3e-7, atol=1e-8)
-    assert torch.equal(b["centers"].cpu(), ref_c), (b["centers"].cpu() - ref_c).abs().max()
+    if c % 8 == 0:                               # ATen's contiguous-row norm: 8 vector lanes, then the lanes in order
+        assert torch.equal(b["centers"].cpu(), ref_c), (b["centers"].cpu() - ref_c).abs().max()
+    else:                                        # widths with a vector tail (no reference config): to rounding
+        torch.testing.assert_close(b["centers"].cpu(), ref_c, rtol=3e-7, atol=1e-8)
 
 
 def test_channel_major_maps(eng):
