@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define VR_ABI_VERSION 2
+#define VR_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define VR_API __attribute__((visibility("default")))
@@ -73,6 +73,9 @@ typedef struct vr_ctx vr_ctx;
 /* Library / device -------------------------------------------------------------------- */
 VR_API int vr_abi_version(void);
 VR_API const char* vr_last_error(void);
+/* The dummy point's mass of partial OT, 1 - ot_part, rounded as utilities/diml.py:61 rounds it (double subtraction of the
+ * Python float, one rounding to fp32); ot_part travels as fp32, the decimal the caller typed is recovered.  Host arithmetic. */
+VR_API float vr_partial_ot_pad(float ot_part);
 /* Creates a context bound to CUDA device `device` (queries SM count, cluster support). */
 VR_API int vr_create(int device, vr_ctx** out);
 VR_API int vr_destroy(vr_ctx* ctx);

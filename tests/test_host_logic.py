@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/vitrerank.h but not exported"
     assert set(_lib.EXPORTS) == set(names), "ctypes binding and header disagree"
-    assert _lib.lib.vr_abi_version() == 2
+    assert _lib.lib.vr_abi_version() == 3
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
@@ -152,6 +152,9 @@ def test_dropin_import_surface():
     import inspect
     import utilities.diml as D
     import evaluation.eval_cvt_diml as E
+    import evaluation.eval_diml as E_res
+    import evaluation.eval_attn_diml as E_attn
+    import evaluation.eval_swin_diml as E_swin
     import evaluation.metrics as M
     import evaluation  # noqa: F401  (must not need faiss)
     for name in ("Sinkhorn", "Sinkhorn_partial", "calc_similarity", "calc_distance", "calc_similarity_vit",
@@ -180,6 +183,9 @@ def test_signatures_match_the_reference_source():
     import inspect
     import utilities.diml as D
     import evaluation.eval_cvt_diml as E
+    import evaluation.eval_diml as E_res
+    import evaluation.eval_attn_diml as E_attn
+    import evaluation.eval_swin_diml as E_swin
     import evaluation.metrics as M
 
     def ref_sigs(path):
@@ -201,6 +207,9 @@ def test_signatures_match_the_reference_source():
                              (E, "evaluation/eval_cvt_diml.py", ["evaluate", "evaluate_patch_similarity",
                                                                  "get_attention_rollout", "filter_attention_map",
                                                                  "resize_attn_map"]),
+                             (E_res, "evaluation/eval_diml.py", ["evaluate"]),          # the sibling callers of the same loop
+                             (E_attn, "evaluation/eval_attn_diml.py", ["evaluate"]),
+                             (E_swin, "evaluation/eval_swin_diml.py", ["evaluate"]),
                              (M, "evaluation/metrics.py", ["get_metrics", "get_metrics_rank"])):
         sigs = ref_sigs(os.path.join(REF, path))
         for n in names:
@@ -309,3 +318,18 @@ def test_bank_file_roundtrip_and_rejects_damage(tmp_path):
         B.load(bad)
     with pytest.raises(B.BankFileError):
         B.save(bad, g.patches, g.centers[:5])
+
+
+def test_partial_ot_pad_is_the_reference_rounding():
+    """diml.py:61 forms `K.new_tensor(1 - ot_part)`: a double subtraction of the Python float, rounded once to fp32.  The
+    ABI carries ot_part as fp32; vr_partial_ot_pad recovers the decimal the caller typed.  (Host arithmetic: runs without a GPU.)"""
+    import ctypes as C
+    from vitrerank import _lib
+    for i in range(0, 1000):
+        part = i / 1000.0
+        want = np.float32(1 - part)
+        got = np.float32(_lib.lib.vr_partial_ot_pad(C.c_float(part)))
+        assert got == want, (part, got, want)
+    for part in (0.123456, 0.3333333, 1 / 3, 0.7071067811865476):
+        got = np.float32(_lib.lib.vr_partial_ot_pad(C.c_float(part)))
+        assert abs(float(got) - (1 - part)) < 1e-7

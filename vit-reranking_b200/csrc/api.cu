@@ -81,6 +81,8 @@ extern "C" {
 
 int vr_abi_version(void) { return VR_ABI_VERSION; }
 
+float vr_partial_ot_pad(float ot_part) { return partial_ot_bin(ot_part); }
+
 const char* vr_last_error(void) { return g_err; }
 
 int64_t vr_take_launch_count(void) {

@@ -36,6 +36,7 @@ def _load():
     sig = {
         "vr_abi_version": (C.c_int, []),
         "vr_last_error": (C.c_char_p, []),
+        "vr_partial_ot_pad": (C.c_float, [C.c_float]),
         "vr_create": (C.c_int, [C.c_int, P(vp)]),
         "vr_destroy": (C.c_int, [vp]),
         "vr_device_info": (C.c_int, [vp, P(i32), P(i32)]),
