@@ -64,7 +64,9 @@ def evaluate_sharded(engine, trunc_nums, params, gather_niter=False):
     return tallies, niter
 
 
-HOST_PIECES = 4   # upload / all-gather pipeline depth of evaluate_host_sharded
+import os as _os
+
+HOST_PIECES = int(_os.environ.get("VR_HOST_PIECES", "8"))   # upload / all-gather / re-pack pipeline depth of evaluate_host_sharded
 
 
 def evaluate_host_sharded(engine, patches, centers, rollout, labels, trunc_nums, params):
@@ -75,7 +77,7 @@ def evaluate_host_sharded(engine, patches, centers, rollout, labels, trunc_nums,
     With W ranks every image crosses PCIe once per node: the gallery is cut into HOST_PIECES pieces of W slices; rank r
     uploads slice r of every piece on a copy stream, each piece is all-gathered in place over NVLink as soon as its
     slices have landed (while the next piece is still in flight on PCIe) and re-packed into the operand layout of the
-    fused kernel (vr_bank_prepare) on the same side stream.  Stage 0 needs only the centres and runs meanwhile on the
+    fused kernel (vr_bank_prepare) on a third stream, under the all-gather of the next piece.  Stage 0 needs only the centres and runs meanwhile on the
     main stream; the rerank waits for the last piece."""
     import torch.distributed as dist
     rank, w = world()
@@ -94,17 +96,42 @@ def evaluate_host_sharded(engine, patches, centers, rollout, labels, trunc_nums,
     st = getattr(engine, "_host_shard_state", None)
     if st is None or st["shape"] != (total, c, r):
         st = dict(shape=(total, c, r), buf=torch.empty(total, c, r, dtype=torch.float32, device=dev),
-                  copy=torch.cuda.Stream(dev), side=torch.cuda.Stream(dev),
-                  landed=[torch.cuda.Event() for _ in range(pieces)], ready=torch.cuda.Event())
+                  copy=torch.cuda.Stream(dev), side=torch.cuda.Stream(dev), prep=torch.cuda.Stream(dev),
+                  landed=[torch.cuda.Event() for _ in range(pieces)], gathered=[torch.cuda.Event() for _ in range(pieces)],
+                  ready=torch.cuda.Event())
         engine._host_shard_state = st
-    buf, copy_stream, side = st["buf"], st["copy"], st["side"]
+    buf, copy_stream, side, prep = st["buf"], st["copy"], st["side"], st["prep"]
     cur = torch.cuda.current_stream(dev)
     copy_stream.wait_stream(cur)               # the previous pass is done with the buffer
     side.wait_stream(cur)
-    labels_d = labels.to(dev, non_blocking=True)
-    centers_d = centers.to(dev, non_blocking=True)
-    rollout_d = None if rollout is None else rollout.to(dev, non_blocking=True)
-    h2d = small
+    prep.wait_stream(cur)
+    # the small banks (centres, rollout, labels: 43 MB at SOP scale) go up whole on every rank.  Sharding them too
+    # (VR_SHARD_SMALL=1: 1/W each + three all-gathers before stage 0) saves PCIe bytes -- with 8 ranks pulling from one host the
+    # aggregate is ~190 GB/s -- but measured 5 ms SLOWER per pass on 2 GPUs (78.1 -> 83.0 ms): the collectives put a rank
+    # rendezvous in front of stage 0.  Off by default.
+    ms = (n + w - 1) // w
+    sm_ = st.get("small")
+    if sm_ is None or sm_["n"] != n or (sm_["r"] is None) != (rollout is None):
+        sm_ = dict(n=n, c=torch.empty(w * ms, c, dtype=torch.float32, device=dev),
+                   r=None if rollout is None else torch.empty(w * ms, r, dtype=torch.float32, device=dev),
+                   l=torch.zeros(w * ms, dtype=torch.int64, device=dev))
+        st["small"] = sm_
+    slo, shi = rank * ms, min(n, (rank + 1) * ms)
+    h2d = 0
+    shard_small = _os.environ.get("VR_SHARD_SMALL", "0") == "1"
+    for dst, src in ((sm_["c"], centers), (sm_["r"], rollout), (sm_["l"], labels)):
+        if dst is None:
+            continue
+        if not shard_small:
+            dst[:n].copy_(src, non_blocking=True)
+            h2d += src.numel() * src.element_size()
+            continue
+        if shi > slo:
+            dst[slo:shi].copy_(src[slo:shi], non_blocking=True)
+            h2d += (shi - slo) * src[0].numel() * src.element_size()
+        dist.all_gather_into_tensor(dst.view(-1), dst[slo:slo + ms].reshape(-1))
+    centers_d, labels_d = sm_["c"][:n], sm_["l"][:n]
+    rollout_d = None if rollout is None else sm_["r"][:n]
     with torch.cuda.stream(copy_stream):
         for p in range(pieces):
             lo = (p * w + rank) * mp
@@ -114,16 +141,22 @@ def evaluate_host_sharded(engine, patches, centers, rollout, labels, trunc_nums,
                 h2d += (hi - lo) * c * r * 4
             st["landed"][p].record(copy_stream)
     engine.register(buf[:n], centers_d, rollout_d, labels_d)     # pointers only; the patches are still in flight
+    # three streams, one per resource: PCIe (copy), NVLink (side: the all-gathers), HBM (prep: the re-pack of a gathered piece
+    # runs under the all-gather of the next one)
     with torch.cuda.stream(side):
         for p in range(pieces):
             side.wait_event(st["landed"][p])
             piece = buf[p * w * mp:(p + 1) * w * mp]
             dist.all_gather_into_tensor(piece.view(-1), piece[rank * mp:(rank + 1) * mp].view(-1))   # in place, NVLink
+            st["gathered"][p].record(side)
+    with torch.cuda.stream(prep):
+        for p in range(pieces):
+            prep.wait_event(st["gathered"][p])
             lo = p * w * mp
             hi = min(n, lo + w * mp)
             if hi > lo:
-                engine.prepare_bank(lo, hi - lo, stream=side)
-        st["ready"].record(side)
+                engine.prepare_bank(lo, hi - lo, stream=prep)
+        st["ready"].record(prep)
     kp = max(k, engine.bank["max_num_pos"], 8)
     idx, approx = engine.stage0_topk(kp, q_start=q_start, q_stride=q_stride, nq=nq)
     cur.wait_event(st["ready"])
