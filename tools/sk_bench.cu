@@ -316,6 +316,114 @@ __global__ void __launch_bounds__(256, 1) s3_kernel(int nch, float* out, long lo
     if (tid == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+
+// ---------------- 2b. the same iteration in a HALF-strip layout: 2 rows / 2 columns per lane, one pair per warp (25 of 32
+// lanes), 16 warps per CTA = 4 warps per scheduler at <= 128 registers (the 4-row layout holds 2 warps per scheduler) ----------------
+constexpr int W3_THREADS = 512;
+__global__ void __launch_bounds__(W3_THREADS, 1) halfstrip_kernel(int iters, float* out, long long* cycles) {
+    __shared__ __align__(16) float cs[W2_PAIRS * VP];
+    __shared__ __align__(16) float rs[W2_PAIRS * VP];
+    __shared__ uint32_t tbase;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int pair = warp;
+    const bool active = lane < 25;
+    if (warp == 0) tmem_alloc(&tbase, 512);
+    for (int i = tid; i < W2_PAIRS * VP; i += W3_THREADS) { cs[i] = 1.0f; rs[i] = 1.0f; }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // 4 warps share a TMEM lane quarter: 128 columns each (98 used: [s][2 owned columns])
+    const uint32_t taddr = tbase + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * 128);
+    ull K01[49];
+#pragma unroll
+    for (int m = 0; m < 49; m++) {
+        const float b = 0.01f + 0.001f * ((tid * 7 + m * 13) % 97);
+        K01[m] = pack2(b, b * 1.01f);
+    }
+    for (int m = 0; m < 48; m += 2) {
+        uint32_t kc[4];
+        const float b = 0.01f + 0.001f * ((tid * 7 + m * 13) % 97);
+        kc[0] = __float_as_uint(b); kc[1] = __float_as_uint(b * 1.01f); kc[2] = __float_as_uint(b * 1.02f); kc[3] = __float_as_uint(b * 1.03f);
+        tmem_st4(taddr + 2 * m, kc);
+    }
+    {
+        uint32_t kc[4] = {__float_as_uint(0.02f), __float_as_uint(0.021f), 0u, 0u};
+        tmem_st4(taddr + 96, kc);
+    }
+    tmem_wait_st();
+    const float u0 = 0.02f, v0 = 0.02f;
+    float r0 = 1.f, r1 = 1.f, esum = 0.f;
+    const float4* c4 = reinterpret_cast<const float4*>(cs + pair * VP);
+    const float4* r4 = reinterpret_cast<const float4*>(rs + pair * VP);
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; it++) {
+        // ---- row pass: 49 FFMA2 from registers, 13 LDS.128 (whole warp reads one address: a broadcast) ----
+        float y0, y1;
+        {
+            ull y01 = 0ull;
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                const float4 cv = c4[i];
+                y01 = ffma2(K01[4 * i + 0], pack2(cv.x, cv.x), y01);
+                y01 = ffma2(K01[4 * i + 1], pack2(cv.y, cv.y), y01);
+                y01 = ffma2(K01[4 * i + 2], pack2(cv.z, cv.z), y01);
+                y01 = ffma2(K01[4 * i + 3], pack2(cv.w, cv.w), y01);
+            }
+            const float cl = cs[pair * VP + 48];
+            y01 = ffma2(K01[48], pack2(cl, cl), y01);
+            unpack2(y01, y0, y1);
+        }
+        {
+            const float n0 = u0 / y0, n1 = u0 / y1;
+            esum += fabsf(n0 - r0) + fabsf(n1 - r1);
+            r0 = n0; r1 = n1;
+            if (active) *reinterpret_cast<float2*>(rs + pair * VP + 2 * lane) = make_float2(n0, n1);
+        }
+        __syncwarp();
+        // ---- column pass: 2 owned columns x 49 rows from tensor memory (x16 loads = 8 rows each) ----
+        float x0, x1;
+        {
+            ull x01 = 0ull;
+            uint32_t ka[16], kb[16];
+            tmem_ld16(taddr, ka);
+#pragma unroll
+            for (int i = 0; i < 6; i += 2) {
+                tmem_wait_ld();
+                tmem_ld16(taddr + 16 * (i + 1), kb);
+                {
+                    const float4 ra = r4[2 * i], rb = r4[2 * i + 1];
+                    const float rr[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+                    for (int q = 0; q < 8; q++) x01 = ffma2(pk(ka[2 * q], ka[2 * q + 1]), pack2(rr[q], rr[q]), x01);
+                }
+                tmem_wait_ld();
+                if (i + 2 < 6) tmem_ld16(taddr + 16 * (i + 2), ka);
+                else tmem_ld4(taddr + 96, ka);
+                {
+                    const float4 ra = r4[2 * i + 2], rb = r4[2 * i + 3];
+                    const float rr[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+                    for (int q = 0; q < 8; q++) x01 = ffma2(pk(kb[2 * q], kb[2 * q + 1]), pack2(rr[q], rr[q]), x01);
+                }
+            }
+            tmem_wait_ld();
+            const float rl = rs[pair * VP + 48];
+            x01 = ffma2(pk(ka[0], ka[1]), pack2(rl, rl), x01);
+            unpack2(x01, x0, x1);
+        }
+        if (active) *reinterpret_cast<float2*>(cs + pair * VP + 2 * lane) = make_float2(v0 / x0, v0 / x1);
+        __syncwarp();
+    }
+    const long long t1 = clock64();
+    __syncthreads();
+    if (tid == 0) cycles[blockIdx.x] = t1 - t0;
+    out[blockIdx.x * W3_THREADS + tid] = esum + r0 + cs[pair * VP + (lane & 15)];
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, 512);
+}
+
 int main() {
     const int blocks = 148;
     float* out;
@@ -348,6 +456,15 @@ int main() {
         mean /= blocks;
         const char* sn[3] = {"FFMA2 + TMEM columns", "FFMA  + TMEM columns", "FFMA2, no TMEM (bound)"};
         printf("strip %-24s: %.1f cycles per iteration per CTA (16 pairs) = %.1f cycles per pair-iteration\n", sn[mode], mean, mean / 16);
+    }
+    {
+        halfstrip_kernel<<<blocks, W3_THREADS>>>(iters, out, cyc);
+        CHECK(cudaDeviceSynchronize());
+        CHECK(cudaMemcpy(h, cyc, blocks * 8, cudaMemcpyDeviceToHost));
+        double mean = 0;
+        for (int i = 0; i < blocks; i++) mean += (double)h[i] / iters;
+        mean /= blocks;
+        printf("strip %-24s: %.1f cycles per iteration per CTA (16 pairs) = %.1f cycles per pair-iteration\n", "HALF strips, 16 warps", mean, mean / 16);
     }
     for (int mode = 0; mode < 3; mode++) {
         const int nch = 4096;

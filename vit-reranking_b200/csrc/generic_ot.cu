@@ -411,9 +411,12 @@ __global__ void copy_niter_kernel(const int32_t* src, int32_t* dst, int64_t n) {
 }
 
 // ---- workspace carving ----------------------------------------------------------------
+constexpr int SKC_T = 8;   // iterations per launch of the chunked solver
+
 struct GenWs {
     float *sim, *K, *u, *v, *rv, *cv, *e;
-    int32_t *done, *niter;
+    float *ehist, *rhist, *chist;   // chunked solver: sum |dr| and the (r, c) state of every iteration of the current chunk
+    int32_t *done, *niter, *tstar;
     size_t bytes;
 };
 
@@ -434,6 +437,10 @@ static GenWs carve(void* base, int64_t nq, int64_t np, int r, int rows, int cols
     w.e = reinterpret_cast<float*>(take((size_t)np * 4));
     w.done = reinterpret_cast<int32_t*>(take((size_t)nq * 4));
     w.niter = reinterpret_cast<int32_t*>(take((size_t)nq * 4));
+    w.tstar = reinterpret_cast<int32_t*>(take((size_t)nq * 4));
+    w.ehist = reinterpret_cast<float*>(take((size_t)np * SKC_T * 4));
+    w.rhist = reinterpret_cast<float*>(take((size_t)np * SKC_T * rows * 4));
+    w.chist = reinterpret_cast<float*>(take((size_t)np * SKC_T * cols * 4));
     w.bytes = off + 256;
     return w;
 }
@@ -641,6 +648,150 @@ __global__ void __launch_bounds__(GI_THREADS, 1) generic_sk_persistent_kernel(Sk
     if (reporter && tid == 0) a.niter[qi] = niter;
 }
 
+// ---- the loop in chunks of SKC_T iterations, no exchange at all ----
+// The pairs of a query only meet in the stop test (the batch mean of |dr|); between tests they evolve independently.  A CTA
+// therefore runs SKC_T iterations of its pair on its own -- K staged once per chunk -- and records sum |dr| AND the (r, c) state
+// of every iteration; `decide` then finds, per query, the first iteration of the chunk whose batch mean is below the threshold,
+// and `select` copies that iteration's state back (or the last one, to continue from).  No CTA waits for another: any number of
+// pairs per query, every SM busy (the persistent kernel above keeps 100 of 148 SMs busy at K = 100 and spends half its warp time
+// behind the exchange poll), at the price of up to SKC_T - 1 iterations run in vain per query.
+struct ChunkArgs {
+    IterArgs it;
+    float *ehist, *rhist, *chist;
+    int32_t* tstar;
+    int it0, max_iter;
+    float* dbg_err;
+};
+
+__global__ void __launch_bounds__(GI_THREADS, 1) generic_sk_chunk_kernel(ChunkArgs p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const IterArgs& a = p.it;
+    const int rows = a.rows, cols = a.cols, ld = skp_ld(cols);
+    const int rp = (rows + 3) & ~3, cp = (cols + 3) & ~3;
+    float* Ks = reinterpret_cast<float*>(smem_raw);   // [rows][ld]
+    float* cs = Ks + (size_t)rows * ld;               // [2][cp]
+    float* rs = cs + 2 * cp;                          // [2][rp]
+    float* us = rs + 2 * rp;                          // [rp]
+    float* vs = us + rp;                              // [cp]
+    float* red = vs + cp;                             // [32]
+    __shared__ __align__(8) uint64_t kbar;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t pair = blockIdx.x;
+    const int64_t qi = pair / a.k;
+    if (a.done[qi] || a.e[pair] < 0.f) return;
+    const float* Kg = a.K + pair * (int64_t)rows * cols;
+    const bool bulk = ld == cols && ((reinterpret_cast<uintptr_t>(Kg) & 15) == 0) && ((size_t)rows * cols * 4 < (1u << 20));
+    if (bulk) {
+        if (tid == 0) {
+            mbar_init(&kbar, 1);
+            fence_mbar_init();
+            mbar_expect_tx(&kbar, (uint32_t)(rows * cols * 4));
+            bulk_g2s(Ks, Kg, (uint32_t)(rows * cols * 4), &kbar);
+        }
+    } else {
+        for (int s = warp; s < rows; s += GI_THREADS / 32) {
+            float* dst = Ks + (size_t)s * ld;
+            const float* src = Kg + (int64_t)s * cols;
+            for (int m = lane; m < ld; m += 32) dst[m] = m < cols ? __ldg(src + m) : 0.f;
+        }
+    }
+    for (int s = tid; s < rows; s += GI_THREADS) {
+        us[s] = a.u[pair * rows + s];
+        rs[rp + s] = a.rv[pair * rows + s];           // r of the iteration before this chunk
+    }
+    for (int m = tid; m < cp; m += GI_THREADS) {
+        vs[m] = m < cols ? a.v[pair * cols + m] : 0.f;
+        cs[cp + m] = m < cols ? a.cv[pair * cols + m] : 0.f;
+        cs[m] = 0.f;
+    }
+    __syncthreads();
+    if (bulk) mbar_wait(&kbar, 0);
+    const bool fused = (int64_t)rows * cols >= 400;   // torch.bmm's small-matrix path multiplies and adds unfused (see above)
+    const int nt = min(SKC_T, p.max_iter - p.it0);
+    for (int t = 0; t < nt; t++) {
+        const int cur = t & 1, prv = cur ^ 1;
+        float e = 0.f;
+        for (int s = tid; s < rows; s += GI_THREADS) {
+            const float4* Kr = reinterpret_cast<const float4*>(Ks + (size_t)s * ld);
+            const float4* c = reinterpret_cast<const float4*>(cs + prv * cp);
+            float y = 0.f;
+            if (fused) {
+#pragma unroll 4
+                for (int m4 = 0; m4 < cp / 4; m4++) {
+                    const float4 kv = Kr[m4], cv = c[m4];
+                    y = fmaf(kv.x, cv.x, y);
+                    y = fmaf(kv.y, cv.y, y);
+                    y = fmaf(kv.z, cv.z, y);
+                    y = fmaf(kv.w, cv.w, y);
+                }
+            } else {
+                const float* K1 = Ks + (size_t)s * ld;
+                const float* c1 = cs + prv * cp;
+                for (int m = 0; m < cols; m++) y = __fadd_rn(y, __fmul_rn(K1[m], c1[m]));
+            }
+            const float rn = us[s] / y;
+            e += fabsf(rn - rs[prv * rp + s]);
+            rs[cur * rp + s] = rn;
+            p.rhist[(pair * SKC_T + t) * rows + s] = rn;
+        }
+        e = block_reduce_sum(e, red);
+        if (tid == 0) p.ehist[pair * SKC_T + t] = e;
+        for (int m = tid; m < cols; m += GI_THREADS) {
+            const float* r = rs + cur * rp;
+            float x = 0.f;
+            if (fused)
+                for (int s = 0; s < rows; s++) x = fmaf(Ks[(size_t)s * ld + m], r[s], x);
+            else
+                for (int s = 0; s < rows; s++) x = __fadd_rn(x, __fmul_rn(Ks[(size_t)s * ld + m], r[s]));
+            const float cn = vs[m] / x;
+            cs[cur * cp + m] = cn;
+            p.chist[(pair * SKC_T + t) * cols + m] = cn;
+        }
+        __syncthreads();
+    }
+}
+
+// Per query: the first iteration of the chunk whose batch mean of |dr| is below the threshold (diml.py:50-52).
+__global__ void __launch_bounds__(256) generic_sk_decide_chunk_kernel(ChunkArgs p) {
+    __shared__ float red[32];
+    const IterArgs& a = p.it;
+    const int64_t qi = blockIdx.x;
+    if (a.done[qi]) {
+        if (threadIdx.x == 0) p.tstar[qi] = -1;   // finished in an earlier chunk: its state is final
+        return;
+    }
+    const int nt = min(SKC_T, p.max_iter - p.it0);
+    int tstar = nt - 1, stop = 0;
+    for (int t = 0; t < nt && !stop; t++) {
+        float s = 0.f;
+        for (int i = threadIdx.x; i < a.k; i += 256)
+            if (a.e[qi * a.k + i] >= 0.f) s += p.ehist[(qi * a.k + i) * SKC_T + t];   // NaN / inf propagate: no stop
+        s = block_reduce_sum(s, red);
+        const float mean = s / ((float)a.k * (float)a.rows);
+        if (threadIdx.x == 0 && p.dbg_err) p.dbg_err[qi * p.max_iter + p.it0 + t] = mean;
+        if (mean < a.thresh) {
+            tstar = t;
+            stop = 1;
+        }
+    }
+    if (threadIdx.x == 0) {
+        p.tstar[qi] = tstar;
+        a.niter[qi] = p.it0 + tstar + 1;
+        if (stop) a.done[qi] = 1;
+    }
+}
+
+// Per pair: the state of iteration tstar of the chunk becomes the pair's (r, c) -- final, or the state the next chunk continues from.
+__global__ void __launch_bounds__(128) generic_sk_select_kernel(ChunkArgs p) {
+    const IterArgs& a = p.it;
+    const int64_t pair = blockIdx.x;
+    const int64_t qi = pair / a.k;
+    const int t = p.tstar[qi];
+    if (t < 0 || a.e[pair] < 0.f) return;
+    for (int s = threadIdx.x; s < a.rows; s += 128) a.rv[pair * a.rows + s] = p.rhist[(pair * SKC_T + t) * a.rows + s];
+    for (int m = threadIdx.x; m < a.cols; m += 128) a.cv[pair * a.cols + m] = p.chist[(pair * SKC_T + t) * a.cols + m];
+}
+
 static size_t skp_smem(int rows, int cols) {
     const int ld = skp_ld(cols), rp = (rows + 3) & ~3, cp = (cols + 3) & ~3;
     return ((size_t)rows * ld + 3 * (size_t)cp + 3 * (size_t)rp + 32 + SKP_MAXK) * 4;
@@ -650,7 +801,7 @@ static size_t skp_smem(int rows, int cols) {
 // the iteration / query counts fit the tag.  VR_GENERIC_SK=launches keeps the multi-launch scheme (A/B tests).
 static bool skp_usable(const IterArgs& it, int64_t nq, int max_iter, int* resident_out) {
     const char* e = getenv("VR_GENERIC_SK");
-    if (e && e[0] == 'l') return false;
+    if (!e || e[0] != 'p') return false;   // opt-in: VR_GENERIC_SK=persistent
     const size_t smem = skp_smem(it.rows, it.cols);
     if (smem > 225 * 1024 || it.k > SKP_MAXK || max_iter > 254 || max_iter < 1 || nq >= (1ll << 23)) return false;
     if (cudaFuncSetAttribute(generic_sk_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
@@ -662,12 +813,30 @@ static bool skp_usable(const IterArgs& it, int64_t nq, int max_iter, int* reside
     return per_sm * sms >= it.k;   // the members of a query wait for one another: all must fit on the device
 }
 
-static int run_iterations(const IterArgs& it, int64_t nq, int64_t np, int max_iter, float* dbg_err, cudaStream_t st) {
+static int run_iterations(const IterArgs& it, const GenWs& w, int64_t nq, int64_t np, int max_iter, float* dbg_err, cudaStream_t st) {
     const size_t base = (size_t)(it.rows + it.cols + 32) * 4;
     const size_t staged = base + (size_t)it.rows * (it.cols + 1) * 4;
     const bool use_staged = staged <= 200 * 1024;
     const size_t smem = use_staged ? staged : base;
     VR_REQUIRE(base <= 48 * 1024, "sinkhorn: %d x %d too large", it.rows, it.cols);
+    {   // default: chunks of SKC_T iterations without any exchange (VR_GENERIC_SK=persistent | launches select the others)
+        const char* e = getenv("VR_GENERIC_SK");
+        const size_t smem_c = skp_smem(it.rows, it.cols);
+        if ((!e || e[0] == 'c') && smem_c <= 225 * 1024 && max_iter >= 1) {
+            VR_CHECK_CUDA(cudaFuncSetAttribute(generic_sk_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+            ChunkArgs c{it, w.ehist, w.rhist, w.chist, w.tstar, 0, max_iter, dbg_err};
+            for (int it0 = 0; it0 < max_iter; it0 += SKC_T) {
+                c.it0 = it0;
+                generic_sk_chunk_kernel<<<(unsigned)np, GI_THREADS, smem_c, st>>>(c);
+                VR_LAUNCH_CHECK();
+                generic_sk_decide_chunk_kernel<<<(unsigned)nq, 256, 0, st>>>(c);
+                VR_LAUNCH_CHECK();
+                generic_sk_select_kernel<<<(unsigned)np, 128, 0, st>>>(c);
+                VR_LAUNCH_CHECK();
+            }
+            return VR_OK;
+        }
+    }
     int resident = 0;
     if (skp_usable(it, nq, max_iter, &resident)) {
         SkpArgs p{it, nullptr, max_iter, dbg_err};
@@ -729,7 +898,7 @@ int generic_rerank(GenArgs a, void* ws, size_t ws_bytes, cudaStream_t st) {
     generic_prepare_kernel<<<(unsigned)np, GP_THREADS, smem, st>>>(a);
     VR_LAUNCH_CHECK();
     IterArgs it{w.K, w.u, w.v, w.rv, w.cv, w.e, w.done, w.niter, re, re, a.k, a.p.thresh};
-    int rc = run_iterations(it, a.nq, np, a.p.max_iter, a.dbg_err, st);
+    int rc = run_iterations(it, w, a.nq, np, a.p.max_iter, a.dbg_err, st);
     if (rc) return rc;
     FinishArgs f{w.K, w.sim, w.rv, w.cv, re, re, a.r, a.out_T, a.out_simr, a.out_score};
     generic_finish_kernel<<<(unsigned)np, 256, 0, st>>>(f);
@@ -753,7 +922,7 @@ int generic_sinkhorn(const float* K, const float* u, const float* v, int64_t b, 
     generic_init_kernel<<<(unsigned)((mx + 255) / 256), 256, 0, st>>>(w.rv, w.cv, w.e, b * m, b * n, b, w.done, w.niter, 1);
     VR_LAUNCH_CHECK();
     IterArgs it{K, u, v, w.rv, w.cv, w.e, w.done, w.niter, m, n, (int)b, thresh};
-    int rc = run_iterations(it, 1, b, max_iter, nullptr, st);
+    int rc = run_iterations(it, w, 1, b, max_iter, nullptr, st);
     if (rc) return rc;
     FinishArgs f{K, nullptr, w.rv, w.cv, m, n, 0, T, nullptr, nullptr};
     generic_finish_kernel<<<(unsigned)b, 256, 0, st>>>(f);
