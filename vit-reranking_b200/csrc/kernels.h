@@ -23,6 +23,7 @@ struct PairArgs {
     long long* dbg_clk;       // optional [nq, 16]: phase clocks (only read by builds with -DPR_TIMING)
     unsigned long long* ex_part;   // exchange buffer of the global transport (set by pair_fused_launch)
     int group_ctas;           // CTAs per query of the wide path, ceil(k / 16) (set by pair_fused_launch)
+    int halves;               // half-CTAs (8 pair slots) per query of the packed score-only launch, 0 = whole CTAs (set by pair_fused_launch)
     float part_bin;           // partial OT: 1 - ot_part as the reference rounds it (set by pair_fused_launch)
     const void* c_packed_a;   // re-packed candidate bank (pair_fused_repack) or nullptr: convert on the fly
     const void* q_packed_b;   // re-packed query bank, indexed by the query id
