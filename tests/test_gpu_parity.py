@@ -392,6 +392,30 @@ def test_partial_ot_fused(eng, n, k, flags, nq):
         assert rel_err(mine, d["score"].numpy()).max() < score_gate(niter[q], d["n_iter"]), q
 
 
+@pytest.mark.parametrize("k", [1, 5, 8, 9, 24, 100, 105, 112])
+def test_half_cta_packing_equals_whole_ctas(eng, k):
+    """The score-only pair kernel packs a query's pairs into ceil(k / 8) warp groups that follow one another across CTA
+    boundaries (a CTA may serve two queries); VR_PAIR_HALVES=0 keeps seven whole CTAs per query.  Same arithmetic, same
+    exchange protocol: scores and iteration counts must be bit-identical -- for shortlists that fill warp groups exactly or
+    not, an odd number of queries (the last CTA's second half has no query), full and partial OT."""
+    from vitrerank.engine import OTParams
+    g = synth.make_gallery(400, 128, 49, classes=8, seed=77 + k, sigma=0.6)
+    eng.register(g.patches, g.centers, g.rollout, g.labels)
+    nq = 11
+    idx, approx = eng.stage0_topk(max(k, 8), q_start=3, q_stride=7, nq=nq)
+    for p in (OTParams(mode="rollout"), OTParams(mode="inverse", temperature=0.1, use_cls_token=True),
+              OTParams(mode="rollout", ot_part=0.5)):
+        os.environ.pop("VR_PAIR_HALVES", None)
+        s1, n1 = eng.rerank_scores(idx, k, p, q_start=3, q_stride=7)
+        os.environ["VR_PAIR_HALVES"] = "0"
+        try:
+            s0, n0 = eng.rerank_scores(idx, k, p, q_start=3, q_stride=7)
+        finally:
+            os.environ.pop("VR_PAIR_HALVES", None)
+        assert torch.equal(n1, n0), (p, n1, n0)
+        assert torch.equal(s1, s0), (p, (s1 - s0).abs().max())
+
+
 def test_evaluate_stages_and_scores(eng):
     """Stage by stage on one gallery: shortlist sets, per-pair scores, reranked order."""
     from vitrerank.engine import OTParams
