@@ -91,6 +91,15 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)", 1965.0
 
 
+def tensor_peak():
+    """Dense bf16 / fp16 tensor peak in TFLOP/s: the burst figure of MEASURED_PEAKS.json (a kernel timed alone), else nominal."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst)"
+    except Exception:
+        return 2250.0, "fallback (nominal dense bf16)"
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
 
@@ -388,6 +397,14 @@ def main():
         "clocks": clocks.summary(),
         "gpu_launches": int(launches),
     }
+    if line["detail"]["stage0"]["path"].startswith("tcgen05"):
+        # first stage: two GEMM passes of nq x n x 128 with three fp16 MMAs per product term (hi.hi + lo.hi + hi.lo); the time is
+        # the WHOLE stage (pack, both passes, threshold, final select), so this is a lower bound of the GEMM kernels' own rate
+        tpk, tsrc = tensor_peak()
+        tf = 2.0 * 3.0 * 2.0 * float(nq) * float(n) * float(c) / (s0_ms / 1e3) / 1e12
+        line["roofline_stage0"] = {"bound": "tensor", "kernel": "stage0_mma_kernel (x2) + pack / thresh / final", "achieved": tf,
+                                   "peak": tpk, "unit": "TFLOP/s", "frac": tf / tpk, "peak_source": tsrc, "stage_ms": s0_ms,
+                                   "note": "issued fp16 flops of both passes over the time of the whole stage"}
     if e2e:
         line["e2e"] = e2e
         line["gpu_launches_e2e"] = int(launches_e2e)
