@@ -111,3 +111,14 @@ def test_sop_shape_full(eng):
     assert torch.equal(i1, i0) and torch.equal(s1, s0)
     assert st["overflow_rows"] == 0 and st["fallback_rows"] <= 60, st
     print("sop stage-0 stats", st)
+
+
+def test_few_queries_against_a_large_gallery(eng):
+    """300 queries against 60,502 images: three row blocks, so the gallery is cut into ~29 splits per block (1,856 segment
+    maxima per row: the threshold kernel's long-row path) and every row's candidates arrive in ~116 sub-lists."""
+    n, kp = 60502, 100
+    centers, labels = centers_only(n, classes=11316, seed=1)
+    register_centers(eng, centers, labels)
+    (i1, s1, st), (i0, s0) = both_paths(eng, kp, q_start=5, q_stride=200, nq=300)
+    assert torch.equal(i1, i0) and torch.equal(s1, s0)
+    assert st["overflow_rows"] == 0 and st["fallback_rows"] <= 3, st
