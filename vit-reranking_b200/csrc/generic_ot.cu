@@ -377,6 +377,28 @@ __global__ void __launch_bounds__(256) generic_finish_kernel(FinishArgs a) {
     const float* rv = a.rv + pair * rows;
     const float* cv = a.cv + pair * cols;
     float sc = 0.f;
+    // full-OT score-only calls whose rows are whole float4s (R = 196, 48, ...): a warp per row, 16-byte loads, no index arithmetic
+    if (!a.out_T && !a.out_simr && a.sim && rows == R && cols == R && (R & 3) == 0 &&
+        ((reinterpret_cast<uintptr_t>(a.K) | reinterpret_cast<uintptr_t>(a.sim) | reinterpret_cast<uintptr_t>(a.cv)) & 15) == 0) {
+        const float* sim = a.sim + pair * (int64_t)R * R;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int s = warp; s < R; s += 8) {
+            const float rs = rv[s];
+            const float4* K4 = reinterpret_cast<const float4*>(K + (int64_t)s * R);
+            const float4* S4 = reinterpret_cast<const float4*>(sim + (int64_t)s * R);
+            const float4* C4 = reinterpret_cast<const float4*>(cv);
+            for (int m4 = lane; m4 < R / 4; m4 += 32) {
+                const float4 k = __ldcs(K4 + m4), x = __ldcs(S4 + m4), c = C4[m4];
+                sc += ((rs * c.x) * k.x) * x.x;
+                sc += ((rs * c.y) * k.y) * x.y;
+                sc += ((rs * c.z) * k.z) * x.z;
+                sc += ((rs * c.w) * k.w) * x.w;
+            }
+        }
+        sc = block_reduce_sum(sc, red);
+        if (threadIdx.x == 0 && a.out_score) a.out_score[pair] = sc;
+        return;
+    }
     for (int i = threadIdx.x; i < rows * cols; i += 256) {
         const int s = i / cols, m = i % cols;
         const float T = (rv[s] * cv[m]) * K[i];
@@ -630,10 +652,22 @@ __global__ void __launch_bounds__(GI_THREADS, 1) generic_sk_persistent_kernel(Sk
         for (int m = tid; m < cols; m += GI_THREADS) {
             const float* r = rs + cur * rp;
             float x = 0.f;
-            if (fused)
-                for (int s = 0; s < rows; s++) x = fmaf(Ks[(size_t)s * ld + m], r[s], x);
-            else
+            if (fused) {   // r by float4: a broadcast LDS.32 per row would cost the load pipe as much as K itself
+                const float4* r4 = reinterpret_cast<const float4*>(r);
+                const float* Kc = Ks + m;
+                int s = 0;
+#pragma unroll 2
+                for (; s + 4 <= rows; s += 4) {
+                    const float4 rr = r4[s >> 2];
+                    x = fmaf(Kc[(size_t)(s + 0) * ld], rr.x, x);
+                    x = fmaf(Kc[(size_t)(s + 1) * ld], rr.y, x);
+                    x = fmaf(Kc[(size_t)(s + 2) * ld], rr.z, x);
+                    x = fmaf(Kc[(size_t)(s + 3) * ld], rr.w, x);
+                }
+                for (; s < rows; s++) x = fmaf(Kc[(size_t)s * ld], r[s], x);
+            } else {
                 for (int s = 0; s < rows; s++) x = __fadd_rn(x, __fmul_rn(Ks[(size_t)s * ld + m], r[s]));
+            }
             cs[cur * cp + m] = vs[m] / x;
         }
         __syncthreads();
@@ -739,10 +773,22 @@ __global__ void __launch_bounds__(GI_THREADS, 1) generic_sk_chunk_kernel(ChunkAr
         for (int m = tid; m < cols; m += GI_THREADS) {
             const float* r = rs + cur * rp;
             float x = 0.f;
-            if (fused)
-                for (int s = 0; s < rows; s++) x = fmaf(Ks[(size_t)s * ld + m], r[s], x);
-            else
+            if (fused) {   // r by float4: a broadcast LDS.32 per row would cost the load pipe as much as K itself
+                const float4* r4 = reinterpret_cast<const float4*>(r);
+                const float* Kc = Ks + m;
+                int s = 0;
+#pragma unroll 2
+                for (; s + 4 <= rows; s += 4) {
+                    const float4 rr = r4[s >> 2];
+                    x = fmaf(Kc[(size_t)(s + 0) * ld], rr.x, x);
+                    x = fmaf(Kc[(size_t)(s + 1) * ld], rr.y, x);
+                    x = fmaf(Kc[(size_t)(s + 2) * ld], rr.z, x);
+                    x = fmaf(Kc[(size_t)(s + 3) * ld], rr.w, x);
+                }
+                for (; s < rows; s++) x = fmaf(Kc[(size_t)s * ld], r[s], x);
+            } else {
                 for (int s = 0; s < rows; s++) x = __fadd_rn(x, __fmul_rn(Ks[(size_t)s * ld + m], r[s]));
+            }
             const float cn = vs[m] / x;
             cs[cur * cp + m] = cn;
             p.chist[(pair * SKC_T + t) * cols + m] = cn;
