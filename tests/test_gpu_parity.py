@@ -583,7 +583,7 @@ def test_evaluate_host_sharded_two_rank_nccl(tmp_path):
         assert p.wait(timeout=300) == 0
     got = json.load(open(out))
     np.testing.assert_allclose(np.array(got["t"]), np.array(got["whole"]), rtol=1e-12)
-    # 4 pieces x 2 slices of 38 images: rank 0 uploads slices 0, 2, 4, 6 = 152 images
+    # 8 pieces x 2 slices of 19 images: rank 0 uploads the even slices = 152 images
     assert got["h2d"] == 152 * 128 * 49 * 4 + 301 * 128 * 4 + 301 * 49 * 4 + 301 * 8
 
 
