@@ -416,6 +416,59 @@ def test_half_cta_packing_equals_whole_ctas(eng, k):
         assert torch.equal(s1, s0), (p, (s1 - s0).abs().max())
 
 
+@pytest.mark.parametrize("c,r", [(768, 196), (64, 36), (48, 130)])
+def test_generic_operand_copy_equals_on_the_fly_split(eng, c, r, monkeypatch):
+    """The generic path's S3 reads a registered bank from its pre-split operand copy (generic_repack: TMA + MMA only);
+    VR_GENERIC_PACK=0 splits every pair's rows on the fly.  Same halves, same MMA order: bit-identical scores -- also after
+    the bank is registered again with other contents (the copy must be rebuilt), one and two row tiles, ragged R.
+    (VR_GENERIC_FUSED=0: the separate S3 / S4 kernels on both sides.)"""
+    from vitrerank.engine import OTParams
+    monkeypatch.setenv("VR_GENERIC_FUSED", "0")
+    k, nq = 6, 5
+    for seed in (3, 4):
+        g = synth.make_gallery(40, c, r, classes=4, seed=seed, sigma=0.6)
+        eng.register(g.patches, g.centers, g.rollout, g.labels)
+        idx, _ = eng.stage0_topk(8, q_start=1, q_stride=3, nq=nq)
+        for p in (OTParams(mode="rollout"), OTParams(mode="uniform", ot_part=0.6)):
+            monkeypatch.delenv("VR_GENERIC_PACK", raising=False)
+            s1, n1 = eng.rerank_scores(idx, k, p, q_start=1, q_stride=3)
+            monkeypatch.setenv("VR_GENERIC_PACK", "0")
+            s0, n0 = eng.rerank_scores(idx, k, p, q_start=1, q_stride=3)
+            monkeypatch.delenv("VR_GENERIC_PACK", raising=False)
+            assert torch.equal(n1, n0), (p, n1, n0)
+            assert torch.equal(s1, s0), (p, (s1 - s0).abs().max())
+
+
+@pytest.mark.parametrize("c,r,k,nq", [(768, 196, 10, 6), (64, 36, 7, 9), (48, 130, 5, 4), (32, 49, 200, 3)])
+def test_generic_fused_equals_separate_kernels(eng, c, r, k, nq, monkeypatch):
+    """generic_fused.cu (S3 + S4 in one kernel, a score per iteration, the stop decided afterwards) against the separate
+    kernels of generic_ot.cu (VR_GENERIC_FUSED=0): the same K, the same FMA chains and the same stop arithmetic, so the
+    iteration counts must be IDENTICAL and the scores equal up to the order of the final sum -- for loops that stop in
+    the first pass of 8 iterations, in a later one (the work list), or never (max_iter not a multiple of 8), padded
+    shortlist entries, more candidates per query than SMs, rollout and uniform marginals."""
+    from vitrerank.engine import OTParams
+    n = max(60, k + 20)
+    g = synth.make_gallery(n, c, r, classes=5, seed=c + r, sigma=0.6)
+    eng.register(g.patches, g.centers, g.rollout, g.labels)
+    idx, _ = eng.stage0_topk(k, q_start=2, q_stride=3, nq=nq)
+    idx = idx.clone()
+    idx[1, k - 2:] = -1                                   # padded entries take no part in the stop test and score 0
+    longest = 0
+    for p in (OTParams(mode="rollout"), OTParams(mode="uniform"), OTParams(mode="rollout", thresh=1e-6),
+              OTParams(mode="rollout", thresh=1e-9, max_iter=19), OTParams(mode="uniform", ot_temp=0.1, thresh=1e-5, max_iter=40)):
+        monkeypatch.delenv("VR_GENERIC_FUSED", raising=False)
+        s1, n1 = eng.rerank_scores(idx, k, p, q_start=2, q_stride=3)
+        monkeypatch.setenv("VR_GENERIC_FUSED", "0")
+        s0, n0 = eng.rerank_scores(idx, k, p, q_start=2, q_stride=3)
+        monkeypatch.delenv("VR_GENERIC_FUSED", raising=False)
+        assert torch.equal(n1, n0), (p, n1, n0)
+        assert (s1[1, k - 2:] == 0).all() and (s0[1, k - 2:] == 0).all()
+        err = ((s1 - s0).abs() / s0.abs().clamp_min(1e-6)).max().item()
+        assert err < 2e-6, (p, err)
+        longest = max(longest, int(n1.max()))
+    assert longest > 16                                   # (some case ran into the third pass)
+
+
 def test_evaluate_stages_and_scores(eng):
     """Stage by stage on one gallery: shortlist sets, per-pair scores, reranked order."""
     from vitrerank.engine import OTParams

@@ -47,6 +47,7 @@ struct vr_ctx {
     bool pending_wait = false;
     float* dbg_err = nullptr;  // see vr_debug_err_trace
     bool packed_valid = false; // the fp16 re-pack of `patches` (arena "packed") matches the registered bank
+    bool gpacked_valid = false; // the same for the generic path's operand copy (arena "gpacked")
     int64_t packed_hi = 0;     // images [0, packed_hi) have been re-packed by vr_bank_prepare calls since the registration
     int32_t* pinned = nullptr; // 16 pinned int32 for small device -> host reads (max num_pos)
 };
@@ -196,6 +197,7 @@ int vr_bank_register(vr_ctx* ctx, const float* patches, const float* centers, co
     ctx->c = c;
     ctx->r = r;
     ctx->packed_valid = false;   // re-packed by vr_bank_prepare, or lazily by the first fused rerank on that call's stream
+    ctx->gpacked_valid = false;
     ctx->packed_hi = 0;
     return VR_OK;
 }
@@ -254,6 +256,7 @@ int vr_bank_ingest(vr_ctx* ctx, const float* tokens, const float* centers_raw, i
     int rc = bank_ingest(tokens, centers_raw, channel_major, ctx->n, first, count, h, w, grid, ctx->c, const_cast<float*>(ctx->patches),
                          centers_raw ? const_cast<float*>(ctx->centers) : nullptr, packed, (cudaStream_t)stream);
     if (rc) return rc;
+    ctx->gpacked_valid = false;   // the bank changed under the generic path's operand copy
     if (fused_shape) {
         ctx->packed_hi = std::max(ctx->packed_hi, first + count);
         if (ctx->packed_hi >= ctx->n) ctx->packed_valid = true;
@@ -385,6 +388,38 @@ static int rerank_scores_impl(vr_ctx* ctx, const float* q_patches, const float* 
     g.out_score = out_score;
     g.out_niter = out_niter;
     g.dbg_err = ctx->dbg_err;
+    // operand copy of the registered bank for the tensor-core S3 of the generic path (both roles, 1.43 MB per image at C = 768,
+    // R = 196): derived once per registration when it fits in 48 GB, else every pair converts its rows on the fly
+    g.packed = nullptr;
+    if (!ext && generic_sim_mma_supported(ctx->c, ctx->r) && !(getenv("VR_GENERIC_PACK") && getenv("VR_GENERIC_PACK")[0] == '0')) {
+        const size_t need = (size_t)ctx->n * generic_packed_image_bytes(ctx->c, ctx->r);
+        if (need <= ((size_t)48 << 30)) {
+            void* gp = nullptr;
+            auto& slot = ctx->arena["gpacked"];
+            if (slot.second >= need && slot.first) {
+                gp = slot.first;
+            } else {
+                if (slot.first) cudaFree(slot.first);
+                slot.first = nullptr;
+                slot.second = 0;
+                ctx->gpacked_valid = false;
+                if (cudaMalloc(&gp, need) == cudaSuccess) {
+                    slot.first = gp;
+                    slot.second = need;
+                } else {
+                    (void)cudaGetLastError();   // not enough memory: the converter path needs none
+                    gp = nullptr;
+                }
+            }
+            if (gp) {
+                if (!ctx->gpacked_valid) {
+                    if ((rc = generic_repack(ctx->patches, ctx->n, ctx->c, ctx->r, gp, st))) return rc;
+                    ctx->gpacked_valid = true;
+                }
+                g.packed = gp;
+            }
+        }
+    }
     return generic_rerank(g, workspace, workspace_bytes, st);
 }
 

@@ -933,6 +933,17 @@ int generic_rerank(GenArgs a, void* ws, size_t ws_bytes, cudaStream_t st) {
     a.sim = w.sim; a.K = w.K; a.u = w.u; a.v = w.v; a.rv = w.rv; a.cv = w.cv; a.e = w.e;
     a.done = w.done; a.niter = w.niter;
     a.sim_done = 0;
+    if (a.packed && !a.out_T && !a.out_simr && !a.out_u && !a.out_cc && generic_fused_supported(a.c, a.r, &a.p) &&
+        (a.p.mode != VR_MODE_ROLLOUT || a.c_rollout)) {
+        // registered bank with its operand copy, scores only: S3 and S4 in one kernel, nothing but the scores leaves the SMs
+        int rc = generic_fused_rerank(a, w.done, w.tstar, reinterpret_cast<int32_t*>(w.e), w.ehist, w.rhist, w.niter, st);
+        if (rc) return rc;
+        if (a.out_niter) {
+            copy_niter_kernel<<<(unsigned)((a.nq + 255) / 256), 256, 0, st>>>(w.niter, a.out_niter, a.nq);
+            VR_LAUNCH_CHECK();
+        }
+        return VR_OK;
+    }
     if (generic_sim_mma_supported(a.c, a.r)) {   // S3 on the tensor cores (C % 16 == 0, R <= 256)
         int rc = generic_sim_mma(a, re, st);
         if (rc) return rc;

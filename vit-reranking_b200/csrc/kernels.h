@@ -42,6 +42,7 @@ struct GenArgs {
     int k, c, r;
     vr_ot_params p;
     float part_bin;   // 1 - ot_part as the reference rounds it (set by generic_rerank)
+    const void* packed; // re-packed registered bank for generic_sim_mma (generic_repack), both roles; nullptr: convert per pair
     int sim_done;     // sim and K were written by generic_sim_mma (tensor cores): generic_prepare_kernel skips its fp32 loop
     // workspace
     float* sim;    // [np, r, r]
@@ -101,6 +102,13 @@ int generic_sinkhorn(const float* K, const float* u, const float* v, int64_t b, 
 // generic_s3.cu
 bool generic_sim_mma_supported(int c, int r);
 int generic_sim_mma(const GenArgs& g, int re, cudaStream_t st);
+size_t generic_packed_image_bytes(int c, int r);
+int generic_repack(const float* patches, int64_t n, int c, int r, void* packed, cudaStream_t st);
+
+// generic_fused.cu: S3 + S4 in one kernel from the re-packed bank (full OT, rollout / uniform marginals, scores only)
+bool generic_fused_supported(int c, int r, const vr_ot_params* p);
+int generic_fused_rerank(const GenArgs& g, int32_t* list0, int32_t* list1, int32_t* counts, float* ehist, float* shist,
+                         int32_t* niter, cudaStream_t st);
 
 // finalize.cu
 size_t finalize_workspace_bytes(int64_t nq, int n_trunc);
