@@ -62,7 +62,8 @@ def static_config(workload, n, c, r, k, truncs, mode):
     return {"workload": WORKLOADS[workload][4], "name": workload, "n": n, "c": c, "r": r, "k": k,
             "trunc_nums": list(truncs), "marginals": mode, "queries_per_step": n,
             "l2": "inputs larger than L2 (patch bank %.0f MB, re-packed operand bank %.0f MB)" %
-                  (n * c * r * 4 / 1e6, n * 65536 / 1e6 if (c, r) == (128, 49) else 0.0)}
+                  (n * c * r * 4 / 1e6, n * 65536 / 1e6 if (c, r) == (128, 49) else
+                   (n * c * ((r + 15) // 16 * 16) * 4 / 1e6 if c % 16 == 0 and r <= 224 else 0.0))}
 
 
 def static_traffic(workload, pairs_per_launch):
@@ -367,6 +368,12 @@ def main():
     fp32_achieved = fma_per_launch / (pf_ms / 1e3) / 1e12
     traffic, traffic_file = static_traffic(args.workload, pairs_per_launch)
     scale = n / 100.0
+    if (c, r) == (128, 49) and k <= 1024:
+        kname = "pair_fused_kernel"
+    elif params.mode in ("rollout", "uniform") and params.ot_part > 0.999 and c % 16 == 0 and 20 <= r <= 224:
+        kname = "generic_fused_kernel"          # S3 + S4 in one kernel from the operand copy (generic_fused.cu)
+    else:
+        kname = "generic_sim_mma_kernel + generic_sk_chunk_kernel + generic_finish_kernel"
     line = {
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
         "warmup": warm, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
@@ -381,7 +388,7 @@ def main():
                    "stage0": dict(s0_stats, path="tcgen05 GEMM + fused select (stage0_mma.cu)" if os.environ.get("VR_STAGE0", "") != "sgemm"
                                   and c == 128 and nq >= 256 and kp <= 256 else "fp32 (stage0_topk.cu)"),
                    "sm_count": eng.sm_count, "pair_transport": os.environ.get("VR_PAIR_TRANSPORT", "global")},
-        "roofline": {"bound": "hbm", "kernel": "pair_fused_kernel", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "traffic_source": (f"static: ncu --set full capture of this workload and launch size, profiles/{traffic_file}"
                                         if traffic is not None else None),
@@ -390,13 +397,24 @@ def main():
                      "kernel_ms": pf_ms, "kernel_share_of_step": pf_ms / (elapsed_ms / args.steps),
                      "note": "the candidate gather is the only unavoidable HBM traffic (SURVEY 8d); the kernel is bound by "
                              "FP32 issue / latency in the Sinkhorn loop, see roofline_fp32"},
-        "roofline_fp32": {"bound": "fp32", "kernel": "pair_fused_kernel", "achieved": fp32_achieved, "peak": fp32_peak,
+        "roofline_fp32": {"bound": "fp32", "kernel": kname, "achieved": fp32_achieved, "peak": fp32_peak,
                           "unit": "TFMA/s", "frac": fp32_achieved / fp32_peak,
                           "useful_fma_per_pair_iteration": 2 * r * r, "mean_iterations": mean_it,
                           "peak_source": f"{eng.sm_count} SMs x {FP32_LANES_PER_SM} FP32 lanes x {sm_max_mhz:.0f} MHz"},
         "clocks": clocks.summary(),
         "gpu_launches": int(launches),
     }
+    if kname == "generic_fused_kernel":
+        # S3 of the generic path on the tensor cores: 3 fp16 MMAs (hi.hi + hi.lo + lo.hi) over ceil(R / 128) x 128 rows and the
+        # columns padded to 16 -- ISSUED flops, of which 2 R R C per pair are the fp32 product the reference computes
+        tpk, tsrc = tensor_peak()
+        mt, rp16 = (r + 127) // 128, (r + 15) // 16 * 16
+        issued = 3.0 * 2.0 * mt * 128 * rp16 * c * pairs_per_launch
+        line["roofline_tensor"] = {"bound": "tensor", "kernel": kname, "achieved": issued / (pf_ms / 1e3) / 1e12, "peak": tpk,
+                                   "unit": "TFLOP/s", "frac": issued / (pf_ms / 1e3) / 1e12 / tpk, "peak_source": tsrc,
+                                   "useful_tflops": 2.0 * r * r * c * pairs_per_launch / (pf_ms / 1e3) / 1e12,
+                                   "note": "the tensor phase is ~35 % of the kernel's time (profiles/r2_ncu_generic_fused.md); the "
+                                           "Sinkhorn chains (shared-memory load pipe) take ~42 %"}
     if line["detail"]["stage0"]["path"].startswith("tcgen05"):
         # first stage: two GEMM passes of nq x n x 128 with three fp16 MMAs per product term (hi.hi + lo.hi + hi.lo); the time is
         # the WHOLE stage (pack, both passes, threshold, final select), so this is a lower bound of the GEMM kernels' own rate
