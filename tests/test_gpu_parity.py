@@ -469,6 +469,32 @@ def test_generic_fused_equals_separate_kernels(eng, c, r, k, nq, monkeypatch):
     assert longest > 16                                   # (some case ran into the third pass)
 
 
+def test_generic_rerank_runs_in_rounds_when_the_workspace_is_small(eng, monkeypatch):
+    """generic_rerank with less workspace than all queries need at once runs as many queries per round as fit: the same
+    scores and iteration counts as one round, for the separate kernels (2 R^2 floats per pair) and the fused kernel; a
+    workspace below one query's need is refused (VR_E_WORKSPACE)."""
+    from vitrerank.engine import OTParams
+    from vitrerank._lib import VitRerankError, lib
+    import ctypes as C
+    c, r, k, nq = 64, 36, 6, 7
+    g = synth.make_gallery(50, c, r, classes=4, seed=21, sigma=0.6)
+    eng.register(g.patches, g.centers, g.rollout, g.labels)
+    idx, _ = eng.stage0_topk(8, q_start=1, q_stride=2, nq=nq)
+    for fused, p in (("0", OTParams(mode="rollout")), ("0", OTParams(mode="inverse", temperature=0.1, ot_part=0.7)),
+                     ("1", OTParams(mode="rollout"))):
+        monkeypatch.setenv("VR_GENERIC_FUSED", fused)
+        s_all, n_all = eng.rerank_scores(idx, k, p, q_start=1, q_stride=2)
+        ps = p.struct()
+        one = lib.vr_rerank_workspace_bytes(eng._h, 1, k, C.byref(ps))
+        if fused == "1":                                  # (its figure covers the separate kernels' need for one query)
+            one = 4096
+        s_part, n_part = eng.rerank_scores(idx, k, p, q_start=1, q_stride=2, workspace_bytes=int(2.5 * one))
+        assert torch.equal(n_part, n_all) and torch.equal(s_part, s_all), p
+        with pytest.raises(VitRerankError, match="workspace"):
+            eng.rerank_scores(idx, k, p, q_start=1, q_stride=2, workspace_bytes=one // 4)
+    monkeypatch.delenv("VR_GENERIC_FUSED", raising=False)
+
+
 def test_evaluate_stages_and_scores(eng):
     """Stage by stage on one gallery: shortlist sets, per-pair scores, reranked order."""
     from vitrerank.engine import OTParams

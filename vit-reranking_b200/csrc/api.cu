@@ -301,9 +301,43 @@ int vr_stage0_stats(vr_ctx* ctx, uint32_t* out4_host, void* stream) {
     return VR_OK;
 }
 
+// The generic path's operand copy of the registered bank (generic_s3.cu: both MMA roles, c x rp16 x 4 bytes per image -- 639 KB at
+// C = 768, R = 196), allocated on first use when it fits in 48 GB; nullptr: every pair converts its rows on the fly
+// (shape not supported by the tensor-core S3, VR_GENERIC_PACK=0, or no memory).  Contents: ctx->gpacked_valid.
+static void* generic_operand_copy(vr_ctx* ctx) {
+    if (!ctx->patches || !generic_sim_mma_supported(ctx->c, ctx->r)) return nullptr;
+    const char* e = getenv("VR_GENERIC_PACK");
+    if (e && e[0] == '0') return nullptr;
+    const size_t need = (size_t)ctx->n * generic_packed_image_bytes(ctx->c, ctx->r);
+    if (need > ((size_t)48 << 30)) return nullptr;
+    auto& slot = ctx->arena["gpacked"];
+    if (slot.first && slot.second >= need) return slot.first;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return nullptr;
+    if (slot.first) cudaFree(slot.first);
+    slot.first = nullptr;
+    slot.second = 0;
+    ctx->gpacked_valid = false;
+    void* gp = nullptr;
+    if (cudaMalloc(&gp, need) != cudaSuccess) {
+        (void)cudaGetLastError();   // not enough memory: the converter path needs none
+        return nullptr;
+    }
+    slot.first = gp;
+    slot.second = need;
+    return gp;
+}
+
+// A score-only rerank of queries FROM the registered bank takes generic_fused.cu (S3 + S4 in one kernel, 1.6 KB of workspace per pair)
+static bool generic_fused_ready(vr_ctx* ctx, const vr_ot_params* p) {
+    return generic_fused_supported(ctx->c, ctx->r, p) && (p->mode != VR_MODE_ROLLOUT || ctx->rollout) && generic_operand_copy(ctx) != nullptr;
+}
+
 size_t vr_rerank_workspace_bytes(vr_ctx* ctx, int64_t nq, int32_t k, const vr_ot_params* p) {
     if (!ctx || !p || ctx->n <= 0) return 0;
     if (pair_fused_supports(ctx->c, ctx->r, k, p, !ctx->dbg_err) || (!ctx->dbg_err && pair_fused_supports_wide(ctx->c, ctx->r, k, p))) return 256;
+    // (queries from other banks -- vr_rerank_scores_queries -- take the separate kernels: with less than their 2 R^2 floats per
+    // pair for all queries at once they run as many queries per round as fit, never less than one)
+    if (generic_fused_ready(ctx, p)) return std::max(generic_fused_workspace_bytes(nq, k, ctx->r), generic_rerank_workspace_bytes(1, k, ctx->r, p));
     return generic_rerank_workspace_bytes(nq, k, ctx->r, p);
 }
 
@@ -388,36 +422,16 @@ static int rerank_scores_impl(vr_ctx* ctx, const float* q_patches, const float* 
     g.out_score = out_score;
     g.out_niter = out_niter;
     g.dbg_err = ctx->dbg_err;
-    // operand copy of the registered bank for the tensor-core S3 of the generic path (both roles, 1.43 MB per image at C = 768,
-    // R = 196): derived once per registration when it fits in 48 GB, else every pair converts its rows on the fly
+    // operand copy of the registered bank for the tensor-core S3 of the generic path, derived once per registration
     g.packed = nullptr;
-    if (!ext && generic_sim_mma_supported(ctx->c, ctx->r) && !(getenv("VR_GENERIC_PACK") && getenv("VR_GENERIC_PACK")[0] == '0')) {
-        const size_t need = (size_t)ctx->n * generic_packed_image_bytes(ctx->c, ctx->r);
-        if (need <= ((size_t)48 << 30)) {
-            void* gp = nullptr;
-            auto& slot = ctx->arena["gpacked"];
-            if (slot.second >= need && slot.first) {
-                gp = slot.first;
-            } else {
-                if (slot.first) cudaFree(slot.first);
-                slot.first = nullptr;
-                slot.second = 0;
-                ctx->gpacked_valid = false;
-                if (cudaMalloc(&gp, need) == cudaSuccess) {
-                    slot.first = gp;
-                    slot.second = need;
-                } else {
-                    (void)cudaGetLastError();   // not enough memory: the converter path needs none
-                    gp = nullptr;
-                }
+    if (!ext) {
+        void* gp = generic_operand_copy(ctx);
+        if (gp) {
+            if (!ctx->gpacked_valid) {
+                if ((rc = generic_repack(ctx->patches, ctx->n, ctx->c, ctx->r, gp, st))) return rc;
+                ctx->gpacked_valid = true;
             }
-            if (gp) {
-                if (!ctx->gpacked_valid) {
-                    if ((rc = generic_repack(ctx->patches, ctx->n, ctx->c, ctx->r, gp, st))) return rc;
-                    ctx->gpacked_valid = true;
-                }
-                g.packed = gp;
-            }
+            g.packed = gp;
         }
     }
     return generic_rerank(g, workspace, workspace_bytes, st);
@@ -587,13 +601,14 @@ int vr_evaluate_registered(vr_ctx* ctx, int64_t q_start, int64_t q_stride, int64
     int64_t chunk = std::min<int64_t>(nq, std::max<int64_t>(16384, ((int64_t)1 << 30) / ((int64_t)kp * 12)));
     const bool fused = k > 0 && (pair_fused_supports(ctx->c, ctx->r, k, p, !ctx->dbg_err) ||
                                  (!ctx->dbg_err && pair_fused_supports_wide(ctx->c, ctx->r, k, p)));
+    const bool gfused = k > 0 && !fused && generic_fused_ready(ctx, p);
     if (k > 0 && !fused) {
-        size_t per_q = generic_rerank_workspace_bytes(1, k, ctx->r, p);
+        size_t per_q = gfused ? generic_fused_workspace_bytes(1, k, ctx->r) : generic_rerank_workspace_bytes(1, k, ctx->r, p);
         chunk = std::max<int64_t>(1, std::min<int64_t>(chunk, (int64_t)((size_t)1536 * 1024 * 1024 / per_q)));
     }
     void *d_idx, *d_sc, *d_ot, *d_nit, *d_tal, *d_ws0, *d_ws1, *d_ws2;
     size_t ws0 = stage0_workspace_bytes(chunk, ctx->n, ctx->c, kp, ctx->sms);
-    size_t ws1 = k > 0 ? (fused ? 256 : generic_rerank_workspace_bytes(chunk, k, ctx->r, p)) : 256;
+    size_t ws1 = k > 0 ? (fused ? 256 : vr_rerank_workspace_bytes(ctx, chunk, k, p)) : 256;
     size_t ws2 = finalize_workspace_bytes(chunk, n_trunc);
     if ((rc = arena_get(ctx, "ev_idx", (size_t)chunk * kp * 4, &d_idx))) return rc;
     if ((rc = arena_get(ctx, "ev_sc", (size_t)chunk * kp * 4, &d_sc))) return rc;

@@ -442,7 +442,10 @@ struct GenWs {
     size_t bytes;
 };
 
-static GenWs carve(void* base, int64_t nq, int64_t np, int r, int rows, int cols, bool with_sim) {
+// mode 0: the direct Sinkhorn call (K, u, v are the caller's); 1: the rerank path; 2: generic_fused_rerank only (no sim, K or state history:
+// rhist holds the per-iteration scores)
+static GenWs carve(void* base, int64_t nq, int64_t np, int r, int rows, int cols, int mode) {
+    const bool with_sim = mode == 1;
     GenWs w{};
     size_t off = 0;
     auto take = [&](size_t n) {
@@ -461,18 +464,22 @@ static GenWs carve(void* base, int64_t nq, int64_t np, int r, int rows, int cols
     w.niter = reinterpret_cast<int32_t*>(take((size_t)nq * 4));
     w.tstar = reinterpret_cast<int32_t*>(take((size_t)nq * 4));
     w.ehist = reinterpret_cast<float*>(take((size_t)np * SKC_T * 4));
-    w.rhist = reinterpret_cast<float*>(take((size_t)np * SKC_T * rows * 4));
-    w.chist = reinterpret_cast<float*>(take((size_t)np * SKC_T * cols * 4));
+    w.rhist = reinterpret_cast<float*>(take((size_t)np * SKC_T * (mode == 2 ? 1 : rows) * 4));
+    w.chist = reinterpret_cast<float*>(take(mode == 2 ? 0 : (size_t)np * SKC_T * cols * 4));
     w.bytes = off + 256;
     return w;
 }
 
 size_t generic_rerank_workspace_bytes(int64_t nq, int k, int r, const vr_ot_params* p) {
     const int re = (p->ot_part > 0.999f) ? r : r + 1;
-    return carve(nullptr, nq, nq * k, r, re, re, true).bytes;
+    return carve(nullptr, nq, nq * k, r, re, re, 1).bytes;
 }
 
-size_t generic_sinkhorn_workspace_bytes(int64_t b, int m, int n) { return carve(nullptr, 1, b, 0, m, n, false).bytes; }
+// What generic_rerank needs when it takes generic_fused.cu (a.packed set, scores only, generic_fused_supported): 1.6 KB per pair
+// instead of 2 R^2 floats.
+size_t generic_fused_workspace_bytes(int64_t nq, int k, int r) { return carve(nullptr, nq, nq * k, r, r, r, 2).bytes; }
+
+size_t generic_sinkhorn_workspace_bytes(int64_t b, int m, int n) { return carve(nullptr, 1, b, 0, m, n, 0).bytes; }
 
 // ---- the whole loop in ONE launch: a CTA per pair keeps K in shared memory for all iterations ----
 // The multi-launch scheme above re-stages K (154 KB for a 14 x 14 grid) from global memory in every iteration and always issues
@@ -925,16 +932,41 @@ int generic_rerank(GenArgs a, void* ws, size_t ws_bytes, cudaStream_t st) {
     VR_REQUIRE(np < 0x7fffffffll, "generic_rerank: too many pairs in one call (%lld)", (long long)np);
     const int re = (a.p.ot_part > 0.999f) ? a.r : a.r + 1;
     a.part_bin = partial_ot_bin(a.p.ot_part);
-    GenWs w = carve(ws, a.nq, np, a.r, re, re, true);
+    const bool fused = a.packed && !a.out_T && !a.out_simr && !a.out_u && !a.out_cc && generic_fused_supported(a.c, a.r, &a.p) &&
+                       (a.p.mode != VR_MODE_ROLLOUT || a.c_rollout);
+    GenWs w = carve(ws, a.nq, np, a.r, re, re, fused ? 2 : 1);
     if (w.bytes > ws_bytes) {
-        set_error("generic_rerank: workspace %zu < %zu", ws_bytes, w.bytes);
-        return VR_E_WORKSPACE;
+        // not enough for all queries at once: as many per round as fit (the queries of a call are independent problems)
+        int64_t fit = a.nq;
+        while (fit > 1 && carve(nullptr, fit, fit * a.k, a.r, re, re, fused ? 2 : 1).bytes > ws_bytes) fit >>= 1;
+        if (a.nq == 1 || carve(nullptr, fit, fit * a.k, a.r, re, re, fused ? 2 : 1).bytes > ws_bytes) {
+            set_error("generic_rerank: workspace %zu < %zu (one query needs %zu)", ws_bytes, w.bytes,
+                      carve(nullptr, 1, a.k, a.r, re, re, fused ? 2 : 1).bytes);
+            return VR_E_WORKSPACE;
+        }
+        for (int64_t lo = 0; lo < a.nq; lo += fit) {
+            GenArgs b = a;
+            b.nq = std::min(fit, a.nq - lo);
+            b.q_start = a.q_start + lo * a.q_stride;
+            if (a.cand_idx) b.cand_idx = a.cand_idx + lo * a.cand_stride;
+            const int64_t p0 = lo * a.k;
+            if (a.out_score) b.out_score = a.out_score + p0;
+            if (a.out_niter) b.out_niter = a.out_niter + lo;
+            if (a.out_u) b.out_u = a.out_u + p0 * a.r;
+            if (a.out_v) b.out_v = a.out_v + p0 * a.r;
+            if (a.out_T) b.out_T = a.out_T + p0 * re * re;
+            if (a.out_simr) b.out_simr = a.out_simr + p0 * a.r * a.r;
+            if (a.out_cc) b.out_cc = a.out_cc + p0 * a.r;
+            if (a.dbg_err) b.dbg_err = a.dbg_err + lo * a.p.max_iter;
+            int rc = generic_rerank(b, ws, ws_bytes, st);
+            if (rc) return rc;
+        }
+        return VR_OK;
     }
     a.sim = w.sim; a.K = w.K; a.u = w.u; a.v = w.v; a.rv = w.rv; a.cv = w.cv; a.e = w.e;
     a.done = w.done; a.niter = w.niter;
     a.sim_done = 0;
-    if (a.packed && !a.out_T && !a.out_simr && !a.out_u && !a.out_cc && generic_fused_supported(a.c, a.r, &a.p) &&
-        (a.p.mode != VR_MODE_ROLLOUT || a.c_rollout)) {
+    if (fused) {
         // registered bank with its operand copy, scores only: S3 and S4 in one kernel, nothing but the scores leaves the SMs
         int rc = generic_fused_rerank(a, w.done, w.tstar, reinterpret_cast<int32_t*>(w.e), w.ehist, w.rhist, w.niter, st);
         if (rc) return rc;
@@ -970,7 +1002,7 @@ int generic_rerank(GenArgs a, void* ws, size_t ws_bytes, cudaStream_t st) {
 int generic_sinkhorn(const float* K, const float* u, const float* v, int64_t b, int m, int n, int max_iter,
                      float thresh, float* T, int32_t* niter, void* ws, size_t ws_bytes, cudaStream_t st) {
     VR_REQUIRE(b > 0 && m > 0 && n > 0 && b < 0x7fffffffll, "sinkhorn: bad shape [%lld, %d, %d]", (long long)b, m, n);
-    GenWs w = carve(ws, 1, b, 0, m, n, false);
+    GenWs w = carve(ws, 1, b, 0, m, n, 0);
     if (w.bytes > ws_bytes) {
         set_error("sinkhorn: workspace %zu < %zu", ws_bytes, w.bytes);
         return VR_E_WORKSPACE;

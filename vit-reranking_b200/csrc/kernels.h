@@ -94,6 +94,7 @@ int bank_ingest(const float* tokens, const float* centers_raw, int channel_major
 
 // generic_ot.cu
 size_t generic_rerank_workspace_bytes(int64_t nq, int k, int r, const vr_ot_params* p);
+size_t generic_fused_workspace_bytes(int64_t nq, int k, int r);   // when generic_rerank takes generic_fused.cu
 size_t generic_sinkhorn_workspace_bytes(int64_t b, int m, int n);
 int generic_rerank(GenArgs a, void* ws, size_t ws_bytes, cudaStream_t st);
 int generic_sinkhorn(const float* K, const float* u, const float* v, int64_t b, int m, int n, int max_iter,

@@ -250,14 +250,16 @@ class RerankEngine:
         return {"fallback_rows": int(out[0]), "overflow_rows": int(out[3]), "unsplittable": int(out[2])}
 
     # ---- S2-S5a ----------------------------------------------------------------------------
-    def rerank_scores(self, cand_idx, k, params: OTParams, q_start=0, q_stride=1):
+    def rerank_scores(self, cand_idx, k, params: OTParams, q_start=0, q_stride=1, workspace_bytes=None):
+        """workspace_bytes: a smaller workspace than vr_rerank_workspace_bytes asks for (the shape-generic path then runs as
+        many queries per round as fit)."""
         cand_idx = cand_idx.to(device=self.device, dtype=torch.int32).contiguous()
         nq, stride = cand_idx.shape
         ps = params.struct()
         score = torch.empty(nq, k, dtype=torch.float32, device=self.device)
         niter = torch.zeros(nq, dtype=torch.int32, device=self.device)
-        nb = lib.vr_rerank_workspace_bytes(self._h, nq, k, C.byref(ps))
-        ws = self._workspace("s1", nb)
+        nb = lib.vr_rerank_workspace_bytes(self._h, nq, k, C.byref(ps)) if workspace_bytes is None else int(workspace_bytes)
+        ws = self._workspace("s1", nb) if workspace_bytes is None else torch.empty(nb, dtype=torch.uint8, device=self.device)
         check(lib.vr_rerank_scores(self._h, q_start, q_stride, nq, k, _ptr(cand_idx), stride, C.byref(ps),
                                    _ptr(score), _ptr(niter), _ptr(ws), ws.numel(), _stream(self.device)),
               "vr_rerank_scores")
@@ -274,6 +276,10 @@ class RerankEngine:
         score = torch.empty(nq, k, dtype=torch.float32, device=self.device)
         niter = torch.zeros(nq, dtype=torch.int32, device=self.device)
         nb = lib.vr_rerank_workspace_bytes(self._h, nq, k, C.byref(ps))
+        # (for a bank whose own queries take the fused generic kernel that is the small figure; queries from outside take the
+        # separate kernels, which run as many queries per round as the workspace holds: give them up to 2 GB)
+        re = self._bank["r"] + (0 if params.ot_part > 0.999 else 1)
+        nb = max(nb, min(nq * k * (2 * re * re + 20 * re + 64) * 4 + 65536, 2 << 30))
         ws = self._workspace("s1", nb)
         check(lib.vr_rerank_scores_queries(self._h, _ptr(q_patches), _ptr(q_centers), _ptr(q_rollout), nq, k, _ptr(cand_idx),
                                            stride, C.byref(ps), _ptr(score), _ptr(niter), _ptr(ws), ws.numel(),
