@@ -53,6 +53,7 @@ WORKLOADS = {
     "vitb16": ("sop_vitb16", 4096, 100, dict(use_rollout=True, ot_part=1.0),
                "ViT-B/16 shape: C=768, R=196 (14x14), top-100 OT rerank, rollout marginals, 4096-image synthetic gallery"),
 }
+WORKLOADS["sop_vitb16"] = WORKLOADS["vitb16"]   # (alias: BASELINE.json configs[4])
 METRIC = "reranked query-candidate pairs/sec at K=100"
 FP32_LANES_PER_SM = 128
 

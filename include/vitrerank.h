@@ -155,7 +155,13 @@ VR_API int vr_stage0_stats(vr_ctx* ctx, uint32_t* out4_host, void* stream);
  * batch-global stop per query, and the score sum(T * sim) (:142-143/:361-362).
  * cand_idx is [nq, cand_stride] int32 (first k entries of each row are used; -1 entries
  * are skipped and score 0).  out_score is [nq, k]; out_niter (nullable) [nq] receives the
- * number of Sinkhorn iterations each query ran. */
+ * number of Sinkhorn iterations each query ran.
+ * Shapes other than C = 128, R = 49 take the shape-generic kernels.  For a registered bank with C % 16 == 0 and
+ * 20 <= R <= 224 the library keeps an operand copy (fp16 hi / lo halves, C x ceil16(R) x 4 bytes per image, at most
+ * 48 GB, allocated by the first vr_rerank_workspace_bytes / vr_rerank_scores call after a registration); with it,
+ * full OT and rollout / uniform marginals, S3 + S4 run in one kernel and the workspace is 1.6 KB per pair, otherwise
+ * 2 (R + 1)^2 floats per pair.  A smaller workspace than vr_rerank_workspace_bytes returns is legal as long as one
+ * query fits: the queries are then processed in rounds. */
 VR_API size_t vr_rerank_workspace_bytes(vr_ctx* ctx, int64_t nq, int32_t k, const vr_ot_params* p);
 VR_API int vr_rerank_scores(vr_ctx* ctx, int64_t q_start, int64_t q_stride, int64_t nq, int32_t k,
                      const int32_t* cand_idx, int32_t cand_stride, const vr_ot_params* p,
