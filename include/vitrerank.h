@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define VR_ABI_VERSION 3
+#define VR_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define VR_API __attribute__((visibility("default")))
@@ -194,6 +194,26 @@ VR_API int vr_finalize(vr_ctx* ctx, int64_t q_start, int64_t q_stride, int64_t n
  * rank = argsort(ot_score[q] + approx_score[q, :k], descending) (NaN first, ties: lower position first).  No labels needed. */
 VR_API int vr_blend_rank(vr_ctx* ctx, int64_t nq, int32_t k, int32_t kp, const int32_t* approx_idx, const float* approx_score,
                   const float* ot_score, int32_t* out_rank, void* stream);
+
+/* Attention-rollout producer (the input of --use_rollout; evaluation/eval_cvt_diml.py:54-146) ---------------
+ * vr_rollout_block replaces filter_attention_map(probs, discard_ratio, head_fusion) (:74-108) followed by
+ * resize_attn_map(., resize, stage, grid) (:54-71) for one transformer block: probs is the block's attention
+ * [b, heads, ht, wt] fp32 (device); the heads are fused (fusion 1 = max, 2 = min); the n_discard =
+ * int(ht * wt * discard_ratio) smallest entries of every image are found (ties: lower index first) and the UNION of
+ * their coordinates over the batch is zeroed in every image, as the reference's fancy-index assignment does; with
+ * drop_cls (stage 2, :57-58) row 0 and column 0 are then dropped (H = ht - 1, W = wt - 1); both token axes, square
+ * grids, are pooled to grid x grid with AdaptiveAvgPool2d's arithmetic, the key axis first.  out: [b, grid^2, grid^2]
+ * (query cell, key cell).  Workspace: vr_rollout_block_workspace_bytes (the fused map, b * ht * wt floats).
+ * vr_rollout_chain replaces :130-141: mats [n_mats, b, n, n] (the stacked block maps); with use_res the identity is
+ * added and every row divided by its sum (ATen's summation order); joints [n_mats, b, n, n] receives joint[0] =
+ * mats[0], joint[j] = mats[j] joint[j - 1] (every entry one FMA chain over the inner index; the reference's CPU
+ * bmm may round differently).  The marginal of an image is joints[n_mats - 1].mean(1). */
+VR_API size_t vr_rollout_block_workspace_bytes(int64_t b, int32_t ht, int32_t wt, int32_t drop_cls);
+VR_API int vr_rollout_block(vr_ctx* ctx, const float* probs, int64_t b, int32_t heads, int32_t ht, int32_t wt, int32_t drop_cls,
+                     int32_t grid, int64_t n_discard, int32_t fusion, float* out, void* workspace, size_t workspace_bytes,
+                     void* stream);
+VR_API int vr_rollout_chain(vr_ctx* ctx, const float* mats, int32_t n_mats, int64_t b, int32_t n, int32_t use_res, float* joints,
+                     void* stream);
 
 /* Direct calls (the per-call surface of utilities/diml.py) ------------------------------
  * vr_sinkhorn replaces Sinkhorn(K, u, v, iter) (diml.py:42-54) for any [b, m, n] batch:

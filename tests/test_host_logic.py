@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/vitrerank.h but not exported"
     assert set(_lib.EXPORTS) == set(names), "ctypes binding and header disagree"
-    assert _lib.lib.vr_abi_version() == 3
+    assert _lib.lib.vr_abi_version() == 4
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

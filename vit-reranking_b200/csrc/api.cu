@@ -480,6 +480,24 @@ int vr_blend_rank(vr_ctx* ctx, int64_t nq, int32_t k, int32_t kp, const int32_t*
     return blend_rank(nq, k, kp, approx_idx, approx_score, ot_score, out_rank, (cudaStream_t)stream);
 }
 
+size_t vr_rollout_block_workspace_bytes(int64_t b, int32_t ht, int32_t wt, int32_t drop_cls) {
+    if (b <= 0 || ht <= 0 || wt <= 0) return 0;
+    return rollout_block_workspace_bytes(b, ht, wt, drop_cls ? 1 : 0);
+}
+
+int vr_rollout_block(vr_ctx* ctx, const float* probs, int64_t b, int32_t heads, int32_t ht, int32_t wt, int32_t drop_cls, int32_t grid,
+                     int64_t n_discard, int32_t fusion, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+    VR_REQUIRE(ctx, "ctx is null");
+    VR_CHECK_CUDA(cudaSetDevice(ctx->device));
+    return rollout_block(probs, b, heads, ht, wt, drop_cls, grid, n_discard, fusion, out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int vr_rollout_chain(vr_ctx* ctx, const float* mats, int32_t n_mats, int64_t b, int32_t n, int32_t use_res, float* joints, void* stream) {
+    VR_REQUIRE(ctx, "ctx is null");
+    VR_CHECK_CUDA(cudaSetDevice(ctx->device));
+    return rollout_chain(mats, n_mats, b, n, use_res, joints, (cudaStream_t)stream);
+}
+
 size_t vr_sinkhorn_workspace_bytes(int64_t b, int32_t m, int32_t n) { return generic_sinkhorn_workspace_bytes(b, m, n); }
 
 int vr_sinkhorn(const float* K, const float* u, const float* v, int64_t b, int32_t m, int32_t n, int32_t max_iter,

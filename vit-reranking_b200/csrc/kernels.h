@@ -111,6 +111,12 @@ bool generic_fused_supported(int c, int r, const vr_ot_params* p);
 int generic_fused_rerank(const GenArgs& g, int32_t* list0, int32_t* list1, int32_t* counts, float* ehist, float* shist,
                          int32_t* niter, cudaStream_t st);
 
+// rollout.cu: the attention-rollout producer (eval_cvt_diml.py:54-146)
+size_t rollout_block_workspace_bytes(int64_t b, int ht, int wt, int drop_cls);
+int rollout_block(const float* probs, int64_t b, int heads, int ht, int wt, int drop_cls, int grid, int64_t n_discard, int fusion,
+                  float* out, void* ws, size_t ws_bytes, cudaStream_t st);
+int rollout_chain(const float* mats, int n_mats, int64_t b, int n, int use_res, float* joints, cudaStream_t st);
+
 // finalize.cu
 size_t finalize_workspace_bytes(int64_t nq, int n_trunc);
 int finalize(int64_t q_start, int64_t q_stride, int64_t nq, int k, int kp, const int32_t* approx_idx,

@@ -72,19 +72,42 @@ def filter_attention_map(raw_attn, discard_ratio, head_fusion, show_fig=False):
     return out
 
 
+def _rollout_on_device(blocks, grid, use_res):
+    """The producer on the B200 (csrc/rollout.cu through vr_rollout_block / vr_rollout_chain) when every block's attention
+    is an fp32 CUDA tensor with square token grids; None otherwise (the torch statements below then run)."""
+    probs = [blk._probs[0] for _, blk in blocks]
+    if not probs or not all(torch.is_tensor(p) and p.is_cuda and p.dtype == torch.float32 and p.dim() == 4 for p in probs):
+        return None
+    for (si, _), p in zip(blocks, probs):
+        d = 1 if si == 2 else 0
+        for t in (p.size(-2) - d, p.size(-1) - d):
+            side = int(round(t ** .5))
+            if side * side != t or side < grid:
+                return None
+    if grid * grid > 128:
+        return None
+    eng = RerankEngine.get(probs[0].device)
+    mats = torch.stack([eng.rollout_block(p, drop_cls=(si == 2), grid=grid, discard_ratio=0.1, head_fusion='min')
+                        for (si, _), p in zip(blocks, probs)])
+    return list(eng.rollout_chain(mats, use_res=use_res))
+
+
 def get_attention_rollout(model, input, grid=7, use_res=True, display_map=False):
     """[:111-146]: per-block attention (blk._probs[0]) -> min-fused, filtered, pooled to
     grid^2 x grid^2, identity added and row-normalised, then chained with bmm.  Returns the list
-    of joint attentions (one per block); evaluate keeps joint[-1].mean(1)."""
+    of joint attentions (one per block); evaluate keeps joint[-1].mean(1).  Attention on a CUDA device is
+    processed by the library's kernels (rollout.cu), on the CPU by the reference's torch statements."""
     with torch.no_grad():
         model.both_forward(input)
+        blocks = [(si, blk) for si in range(3) for blk in getattr(model, f'stage{si}').blocks]
+        joint = _rollout_on_device(blocks, grid, use_res)
+        if joint is not None:
+            return joint
         resize = nn.AdaptiveAvgPool2d((grid, grid))
         mats = []
-        for si in range(3):
-            stage = getattr(model, f'stage{si}')
-            for i, blk in enumerate(stage.blocks):
-                a = filter_attention_map(blk._probs[0], discard_ratio=0.1, head_fusion='min')
-                mats.append(resize_attn_map(a, resize, si, grid, blk_id=i).detach())
+        for si, blk in blocks:
+            a = filter_attention_map(blk._probs[0], discard_ratio=0.1, head_fusion='min')
+            mats.append(resize_attn_map(a, resize, si, grid).detach())
         mats = torch.stack(mats)
         if use_res:
             eye = torch.eye(mats.size(2), device=mats.device, dtype=mats.dtype)

@@ -54,6 +54,9 @@ def _load():
         "vr_finalize_workspace_bytes": (sz, [vp, i64, i32]),
         "vr_finalize": (C.c_int, [vp, i64, i64, i64, i32, i32, vp, vp, vp, P(i32), i32, vp, vp, vp, sz, vp]),
         "vr_blend_rank": (C.c_int, [vp, i64, i32, i32, vp, vp, vp, vp, vp]),
+        "vr_rollout_block_workspace_bytes": (sz, [i64, i32, i32, i32]),
+        "vr_rollout_block": (C.c_int, [vp, vp, i64, i32, i32, i32, i32, i32, i64, i32, vp, vp, sz, vp]),
+        "vr_rollout_chain": (C.c_int, [vp, vp, i32, i64, i32, i32, vp, vp]),
         "vr_sinkhorn_workspace_bytes": (sz, [i64, i32, i32]),
         "vr_sinkhorn": (C.c_int, [vp, vp, vp, i64, i32, i32, i32, f32, vp, vp, vp, sz, vp]),
         "vr_calc_similarity_workspace_bytes": (sz, [i64, i32, i32, P(OTParamsStruct)]),

@@ -315,6 +315,34 @@ class RerankEngine:
                                 _stream(self.device)), "vr_blend_rank")
         return rank
 
+    # ---- attention-rollout producer (eval_cvt_diml.py:54-146) ----------------------------------------
+    def rollout_block(self, probs, drop_cls, grid=7, discard_ratio=0.1, head_fusion="min"):
+        """filter_attention_map + resize_attn_map of one block (vr_rollout_block): probs [B, heads, T, T'] fp32 on the
+        engine's device -> [B, grid^2, grid^2]."""
+        assert probs.is_cuda and probs.dtype == torch.float32 and probs.dim() == 4
+        probs = probs.contiguous()
+        b, heads, ht, wt = probs.shape
+        d = 1 if drop_cls else 0
+        n_discard = int(ht * wt * discard_ratio)                        # eval_cvt_diml.py:91 (the map still holds the cls row / column)
+        g2 = grid * grid
+        out = torch.empty(b, g2, g2, dtype=torch.float32, device=self.device)
+        nb = lib.vr_rollout_block_workspace_bytes(b, ht, wt, d)
+        ws = self._workspace("ro", nb)
+        check(lib.vr_rollout_block(self._h, _ptr(probs), b, heads, ht, wt, d, grid, n_discard, {"max": 1, "min": 2}[head_fusion],
+                                   _ptr(out), _ptr(ws), ws.numel(), _stream(self.device)), "vr_rollout_block")
+        return out
+
+    def rollout_chain(self, mats, use_res=True):
+        """mats [J, B, n, n] -> joints [J, B, n, n] (vr_rollout_chain): identity + row normalisation when use_res, then the
+        running product joint[j] = mats[j] @ joint[j - 1]."""
+        mats = _f32(mats, self.device)
+        j, b, n, n2 = mats.shape
+        assert n == n2
+        joints = torch.empty_like(mats)
+        check(lib.vr_rollout_chain(self._h, _ptr(mats), j, b, n, int(bool(use_res)), _ptr(joints), _stream(self.device)),
+              "vr_rollout_chain")
+        return joints
+
     # ---- whole pass over the registered (device-resident) gallery ---------------------------------
     def evaluate(self, trunc_nums, params: OTParams, q_start=0, q_stride=1, nq=None, want_niter=False):
         """Tallies [len(trunc_nums), 8] (numpy float64, columns METRIC_COLS; sums, not yet
