@@ -46,8 +46,19 @@ __device__ __forceinline__ float fuse_heads(const float* __restrict__ p, int hea
 }
 
 // PASS 0: fuse the heads, store the fused map, histogram of key bits 31..21.  PASS 1 / 2: histogram of bits 20..10 / 9..0 of the
-// keys that share the prefix found so far.
+// keys that share the prefix found so far.  VEC: 16-byte loads and stores (maps whose size is a multiple of 4 floats).
 template <int PASS>
+__device__ __forceinline__ void ro_count(uint32_t* sh, uint32_t key, uint32_t prefix) {
+    if (PASS == 0) {
+        atomicAdd(&sh[key >> 21], 1u);   // (warp-aggregating equal bins with match.any first was twice as slow: 770 against 381 us)
+    } else if (PASS == 1) {
+        if ((key >> 21) == prefix) atomicAdd(&sh[(key >> 10) & 2047u], 1u);
+    } else {
+        if ((key >> 10) == prefix) atomicAdd(&sh[key & 1023u], 1u);
+    }
+}
+
+template <int PASS, bool VEC>
 __global__ void __launch_bounds__(RO_THREADS) rollout_hist_kernel(const float* __restrict__ probs, float* __restrict__ fused,
                                                                    uint32_t* __restrict__ hist, const RoSelect* __restrict__ sel, int heads,
                                                                    int ht, int wt, int mode) {
@@ -58,20 +69,46 @@ __global__ void __launch_bounds__(RO_THREADS) rollout_hist_kernel(const float* _
     __syncthreads();
     const uint32_t prefix = PASS ? sel[b].prefix : 0u;
     const int64_t base = (int64_t)blockIdx.x * (RO_THREADS * RO_ITEMS);
-    for (int it = 0; it < RO_ITEMS; it++) {
-        const int64_t i = base + (int64_t)it * RO_THREADS + threadIdx.x;
-        if (i >= hw) break;
-        float v;
-        if (PASS == 0) {
-            v = fuse_heads(probs + (int64_t)b * heads * hw + i, heads, hw, mode);
-            fused[(int64_t)b * hw + i] = v;
-        } else {
-            v = fused[(int64_t)b * hw + i];
+    if (VEC) {
+        for (int it = 0; it < RO_ITEMS / 4; it++) {
+            const int64_t i = base + ((int64_t)it * RO_THREADS + threadIdx.x) * 4;
+            if (i >= hw) break;
+            float4 v;
+            if (PASS == 0) {
+                const float* p = probs + (int64_t)b * heads * hw + i;
+                v = __ldcs(reinterpret_cast<const float4*>(p));
+                for (int h = 1; h < heads; h++) {
+                    const float4 x = __ldcs(reinterpret_cast<const float4*>(p + h * hw));
+                    if (mode == 2) {   // torch.min / torch.max propagate NaN
+                        v.x = (x.x < v.x || x.x != x.x) ? x.x : v.x; v.y = (x.y < v.y || x.y != x.y) ? x.y : v.y;
+                        v.z = (x.z < v.z || x.z != x.z) ? x.z : v.z; v.w = (x.w < v.w || x.w != x.w) ? x.w : v.w;
+                    } else {
+                        v.x = (x.x > v.x || x.x != x.x) ? x.x : v.x; v.y = (x.y > v.y || x.y != x.y) ? x.y : v.y;
+                        v.z = (x.z > v.z || x.z != x.z) ? x.z : v.z; v.w = (x.w > v.w || x.w != x.w) ? x.w : v.w;
+                    }
+                }
+                *reinterpret_cast<float4*>(fused + (int64_t)b * hw + i) = v;
+            } else {
+                v = *reinterpret_cast<const float4*>(fused + (int64_t)b * hw + i);
+            }
+            ro_count<PASS>(sh, ordered_bits(v.x), prefix);
+            ro_count<PASS>(sh, ordered_bits(v.y), prefix);
+            ro_count<PASS>(sh, ordered_bits(v.z), prefix);
+            ro_count<PASS>(sh, ordered_bits(v.w), prefix);
         }
-        const uint32_t key = ordered_bits(v);
-        if (PASS == 0) atomicAdd(&sh[key >> 21], 1u);
-        else if (PASS == 1) { if ((key >> 21) == prefix) atomicAdd(&sh[(key >> 10) & 2047u], 1u); }
-        else { if ((key >> 10) == prefix) atomicAdd(&sh[key & 1023u], 1u); }
+    } else {
+        for (int it = 0; it < RO_ITEMS; it++) {
+            const int64_t i = base + (int64_t)it * RO_THREADS + threadIdx.x;
+            if (i >= hw) break;
+            float v;
+            if (PASS == 0) {
+                v = fuse_heads(probs + (int64_t)b * heads * hw + i, heads, hw, mode);
+                fused[(int64_t)b * hw + i] = v;
+            } else {
+                v = fused[(int64_t)b * hw + i];
+            }
+            ro_count<PASS>(sh, ordered_bits(v), prefix);
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < RO_BINS; i += RO_THREADS)
@@ -119,17 +156,33 @@ __global__ void __launch_bounds__(RO_THREADS) rollout_pick_kernel(uint32_t* __re
 }
 
 // mask[i] = 1 where image b discards coordinate i: below the threshold, or equal to it when all equals are taken.
+template <bool VEC>
 __global__ void __launch_bounds__(RO_THREADS) rollout_mask_kernel(const float* __restrict__ fused, const RoSelect* __restrict__ sel,
                                                                    unsigned char* __restrict__ mask, int64_t hw) {
     const int b = blockIdx.y;
     const RoSelect s = sel[b];
     const bool all_eq = s.krem == s.eq;
     const int64_t base = (int64_t)blockIdx.x * (RO_THREADS * RO_ITEMS);
-    for (int it = 0; it < RO_ITEMS; it++) {
-        const int64_t i = base + (int64_t)it * RO_THREADS + threadIdx.x;
-        if (i >= hw) break;
-        const uint32_t key = ordered_bits(fused[(int64_t)b * hw + i]);
-        if (key < s.prefix || (key == s.prefix && all_eq)) mask[i] = 1;
+    auto hit = [&](float v) {
+        const uint32_t key = ordered_bits(v);
+        return key < s.prefix || (key == s.prefix && all_eq);
+    };
+    if (VEC) {
+        for (int it = 0; it < RO_ITEMS / 4; it++) {
+            const int64_t i = base + ((int64_t)it * RO_THREADS + threadIdx.x) * 4;
+            if (i >= hw) break;
+            const float4 v = *reinterpret_cast<const float4*>(fused + (int64_t)b * hw + i);
+            if (hit(v.x)) mask[i] = 1;
+            if (hit(v.y)) mask[i + 1] = 1;
+            if (hit(v.z)) mask[i + 2] = 1;
+            if (hit(v.w)) mask[i + 3] = 1;
+        }
+    } else {
+        for (int it = 0; it < RO_ITEMS; it++) {
+            const int64_t i = base + (int64_t)it * RO_THREADS + threadIdx.x;
+            if (i >= hw) break;
+            if (hit(fused[(int64_t)b * hw + i])) mask[i] = 1;
+        }
     }
 }
 
@@ -164,17 +217,20 @@ __global__ void __launch_bounds__(RO_THREADS) rollout_ties_kernel(const float* _
     }
 }
 
-__device__ __forceinline__ int win_lo(int o, int in, int out) { return (int)(((int64_t)o * in) / out); }
-__device__ __forceinline__ int win_hi(int o, int in, int out) { return (int)((((int64_t)(o + 1)) * in + out - 1) / out); }
+// (o < out <= 16 and in < 2^16: 32-bit arithmetic holds the products)
+__device__ __forceinline__ int win_lo(int o, int in, int out) { return (o * in) / out; }
+__device__ __forceinline__ int win_hi(int o, int in, int out) { return ((o + 1) * in + out - 1) / out; }
 
 // out[b][hp][wp]: the masked fused map pooled over the key axis (rows of ws x ws -> g x g, when ws > g), then over the query axis
-// (hs x hs -> g x g, when hs > g).  One CTA per (hp, image); thread wp < g^2 owns an output: per query row of the window, in
-// row-major order, its key-window sum / kh / kw, accumulated and divided the same way -- AdaptiveAvgPool2d's arithmetic on the CPU.
+// (hs x hs -> g x g, when hs > g).  One CTA per (hp, image): the query rows of the window are staged a few at a time (coalesced, the
+// mask applied), every (row, wp) key-window sum / kh / kw is taken by one thread and kept in shared memory, and thread wp < g^2
+// finally adds its column over the rows in row-major order and divides -- AdaptiveAvgPool2d's arithmetic on the CPU.
 __global__ void __launch_bounds__(RO_THREADS) rollout_pool_kernel(const float* __restrict__ fused, const unsigned char* __restrict__ mask,
-                                                                   float* __restrict__ out, int H, int W, int hs, int ws, int g, int drop, int hsingle) {
-    extern __shared__ float rowbuf[];   // [W]
+                                                                   float* __restrict__ out, int H, int W, int hs, int ws, int g, int drop,
+                                                                   int hsingle, int rc) {
+    extern __shared__ float ro_sm[];
     const int b = blockIdx.y, hp = blockIdx.x, t = threadIdx.x;
-    const int g2h = hs > g ? g * g : H, g2w = ws > g ? g * g : W;   // (an axis that is already g x g, or smaller, is kept)
+    const int g2h = hs > g ? g * g : H, g2w = ws > g ? g * g : W;   // (an axis that is already g x g is kept)
     const int wt = W + drop;
     const int64_t hw = (int64_t)(H + drop) * wt;                     // fused and mask cover the whole map; row / column 0 are skipped
     int hy0, hy1, hx0, hx1;
@@ -186,42 +242,72 @@ __global__ void __launch_bounds__(RO_THREADS) rollout_pool_kernel(const float* _
         hy0 = hp / hs; hy1 = hy0 + 1;
         hx0 = hp % hs; hx1 = hx0 + 1;
     }
-    int wy0 = 0, wy1 = 1, wx0 = 0, wx1 = 1;
+    const int kwh = hx1 - hx0, nrows = (hy1 - hy0) * kwh;
+    float* rows = ro_sm;                       // [rc][W]
+    float* out1 = ro_sm + (size_t)rc * W;      // [nrows][g2w]
+    __shared__ int wwin[RO_THREADS][4];        // the key window of every output cell
     if (t < g2w && ws > g) {
         const int oy = t / g, ox = t % g;
-        wy0 = win_lo(oy, ws, g); wy1 = win_hi(oy, ws, g);
-        wx0 = win_lo(ox, ws, g); wx1 = win_hi(ox, ws, g);
+        wwin[t][0] = win_lo(oy, ws, g); wwin[t][1] = win_hi(oy, ws, g);
+        wwin[t][2] = win_lo(ox, ws, g); wwin[t][3] = win_hi(ox, ws, g);
     }
-    float acc = 0.f;
-    for (int hy = hy0; hy < hy1; hy++)
-        for (int hx = hx0; hx < hx1; hx++) {
-            const int64_t h = (int64_t)hy * hs + hx;
-            __syncthreads();
-            for (int w = t; w < W; w += RO_THREADS) {
-                const int64_t i = (h + drop) * wt + (w + drop);
-                rowbuf[w] = mask[i] ? 0.f : fused[(int64_t)b * hw + i];
-            }
-            __syncthreads();
-            if (t < g2w) {
-                float v;
-                if (ws > g) {
-                    float s = 0.f;
-                    for (int y = wy0; y < wy1; y++)
-                        for (int x = wx0; x < wx1; x++) s += rowbuf[y * ws + x];
-                    v = (s / (float)(wy1 - wy0)) / (float)(wx1 - wx0);   // (ATen: sum / kh / kw)
-                } else {
-                    v = rowbuf[t];
+    for (int r0 = 0; r0 < nrows; r0 += rc) {
+        const int nr = min(rc, nrows - r0);
+        __syncthreads();
+        const bool vec = drop == 0 && (W & 3) == 0;   // rows start on 16-byte boundaries
+        const int lane = t & 31, warp = t >> 5;
+        for (int rr = warp; rr < nr; rr += RO_THREADS / 32) {   // a warp per query row: the row's address is computed once
+            const int ri = r0 + rr;
+            const int64_t h = (int64_t)(hy0 + ri / kwh) * hs + (hx0 + ri % kwh);
+            const float* fr = fused + (int64_t)b * hw + (h + drop) * wt + drop;
+            const unsigned char* mr = mask + (h + drop) * wt + drop;
+            float* dst = rows + (size_t)rr * W;
+            if (vec) {
+#pragma unroll 4
+                for (int w4 = lane; w4 < (W >> 2); w4 += 32) {
+                    float4 v = __ldcs(reinterpret_cast<const float4*>(fr) + w4);
+                    const uchar4 m = *(reinterpret_cast<const uchar4*>(mr) + w4);
+                    if (m.x) v.x = 0.f;
+                    if (m.y) v.y = 0.f;
+                    if (m.z) v.z = 0.f;
+                    if (m.w) v.w = 0.f;
+                    *(reinterpret_cast<float4*>(dst) + w4) = v;
                 }
-                acc += v;
+            } else {
+#pragma unroll 4
+                for (int w = lane; w < W; w += 32) {
+                    const float v = __ldcs(fr + w);
+                    dst[w] = mr[w] ? 0.f : v;
+                }
             }
         }
+        __syncthreads();
+        for (int e = t; e < nr * g2w; e += RO_THREADS) {
+            const int rr = e / g2w, wp = e - rr * g2w;
+            const float* rb = rows + (size_t)rr * W;
+            float v;
+            if (ws > g) {
+                const int wy0 = wwin[wp][0], wy1 = wwin[wp][1], wx0 = wwin[wp][2], wx1 = wwin[wp][3];
+                float s = 0.f;
+                for (int y = wy0; y < wy1; y++)
+                    for (int x = wx0; x < wx1; x++) s += rb[y * ws + x];
+                v = (s / (float)(wy1 - wy0)) / (float)(wx1 - wx0);   // (ATen: sum / kh / kw)
+            } else {
+                v = rb[wp];
+            }
+            out1[(size_t)(r0 + rr) * g2w + wp] = v;
+        }
+    }
+    __syncthreads();
     if (t < g2w) {
+        float acc = 0.f;
+        for (int r = 0; r < nrows; r++) acc += out1[(size_t)r * g2w + t];
         // The reference pools the query axis on a permuted VIEW [B, g^2, hs, hs] whose strides are channels-last: for B >= 2 ATen
         // then runs its channels-last kernel, which divides the window sum ONCE by kh * kw; for B = 1 the view counts as
         // contiguous and the plain kernel divides by kh, then by kw -- as does the channels-last kernel's scalar tail, the
         // channels beyond the last whole vector of 8.  (All equal for the power-of-two windows of every reference model.)
         if (hs > g)
-            acc = (hsingle && t < (g2w & ~7)) ? acc / (float)((hy1 - hy0) * (hx1 - hx0)) : (acc / (float)(hy1 - hy0)) / (float)(hx1 - hx0);
+            acc = (hsingle && t < (g2w & ~7)) ? acc / (float)((hy1 - hy0) * kwh) : (acc / (float)(hy1 - hy0)) / (float)kwh;
         out[((int64_t)b * g2h + hp) * g2w + t] = acc;
     }
 }
@@ -338,28 +424,40 @@ int rollout_block(const float* probs, int64_t b, int heads, int ht, int wt, int 
     VR_CHECK_CUDA(cudaMemsetAsync(w.hist, 0, (size_t)b * RO_BINS * 4, st));
     VR_CHECK_CUDA(cudaMemsetAsync(w.mask, 0, (size_t)hw, st));
     VR_CHECK_CUDA(cudaMemsetAsync(w.sel, 0, (size_t)b * sizeof(RoSelect), st));
-    rollout_hist_kernel<0><<<grid_e, RO_THREADS, 0, st>>>(probs, w.fused, w.hist, w.sel, heads, ht, wt, fusion);
-    VR_LAUNCH_CHECK();
+    const bool vec = (hw & 3) == 0 && (reinterpret_cast<uintptr_t>(probs) & 15) == 0;
+#define RO_HIST(PASS)                                                                                                          \
+    do {                                                                                                                       \
+        if (vec) rollout_hist_kernel<PASS, true><<<grid_e, RO_THREADS, 0, st>>>(probs, w.fused, w.hist, w.sel, heads, ht, wt, fusion); \
+        else rollout_hist_kernel<PASS, false><<<grid_e, RO_THREADS, 0, st>>>(probs, w.fused, w.hist, w.sel, heads, ht, wt, fusion);    \
+        VR_LAUNCH_CHECK();                                                                                                     \
+    } while (0)
+    RO_HIST(0);
     if (n_discard > 0) {
         rollout_pick_kernel<0><<<(unsigned)b, RO_THREADS, 0, st>>>(w.hist, w.sel, (uint32_t)n_discard);
         VR_LAUNCH_CHECK();
-        rollout_hist_kernel<1><<<grid_e, RO_THREADS, 0, st>>>(probs, w.fused, w.hist, w.sel, heads, ht, wt, fusion);
-        VR_LAUNCH_CHECK();
+        RO_HIST(1);
         rollout_pick_kernel<1><<<(unsigned)b, RO_THREADS, 0, st>>>(w.hist, w.sel, 0u);
         VR_LAUNCH_CHECK();
-        rollout_hist_kernel<2><<<grid_e, RO_THREADS, 0, st>>>(probs, w.fused, w.hist, w.sel, heads, ht, wt, fusion);
-        VR_LAUNCH_CHECK();
+        RO_HIST(2);
         rollout_pick_kernel<2><<<(unsigned)b, RO_THREADS, 0, st>>>(w.hist, w.sel, 0u);
         VR_LAUNCH_CHECK();
-        rollout_mask_kernel<<<grid_e, RO_THREADS, 0, st>>>(w.fused, w.sel, w.mask, hw);
+        if (vec) rollout_mask_kernel<true><<<grid_e, RO_THREADS, 0, st>>>(w.fused, w.sel, w.mask, hw);
+        else rollout_mask_kernel<false><<<grid_e, RO_THREADS, 0, st>>>(w.fused, w.sel, w.mask, hw);
         VR_LAUNCH_CHECK();
         rollout_ties_kernel<<<(unsigned)b, RO_THREADS, 0, st>>>(w.fused, w.sel, w.mask, hw);
         VR_LAUNCH_CHECK();
     }
-    const int g2h = hs > grid ? grid * grid : H;
-    const size_t smem = (size_t)W * 4;
-    if (smem > 48 * 1024) VR_CHECK_CUDA(cudaFuncSetAttribute(rollout_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rollout_pool_kernel<<<dim3((unsigned)g2h, (unsigned)b), RO_THREADS, smem, st>>>(w.fused, w.mask, out, H, W, hs, ws_, grid, drop_cls, b >= 2 ? 1 : 0);
+#undef RO_HIST
+    const int g2h = hs > grid ? grid * grid : H, g2w = ws_ > grid ? grid * grid : W;
+    const int kmax = hs > grid ? (hs + grid - 1) / grid + 1 : 1;     // longest window side of the query axis
+    const int nrows_max = kmax * kmax;
+    const int rc = std::max(1, std::min(nrows_max, 4096 / W));      // query rows staged at a time (<= 16 KB: 6 CTAs per SM)
+    const size_t smem = ((size_t)rc * W + (size_t)nrows_max * g2w) * 4;
+    VR_REQUIRE(smem <= 200 * 1024, "rollout_block: %d x %d tokens need %zu bytes of shared memory", H, W, smem);
+    if (smem > 40 * 1024)   // (the kernel also holds 4 KB of static shared memory)
+        VR_CHECK_CUDA(cudaFuncSetAttribute(rollout_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rollout_pool_kernel<<<dim3((unsigned)g2h, (unsigned)b), RO_THREADS, smem, st>>>(w.fused, w.mask, out, H, W, hs, ws_, grid, drop_cls,
+                                                                                     b >= 2 ? 1 : 0, rc);
     VR_LAUNCH_CHECK();
     return VR_OK;
 }
