@@ -54,6 +54,9 @@ WORKLOADS = {
                "ViT-B/16 shape: C=768, R=196 (14x14), top-100 OT rerank, rollout marginals, 4096-image synthetic gallery"),
 }
 WORKLOADS["sop_vitb16"] = WORKLOADS["vitb16"]   # (alias: BASELINE.json configs[4])
+WORKLOADS["vitb16_cc"] = ("sop_vitb16", 4096, 100, dict(use_inverse=True, temperature=0.1, use_cls_token=True, ot_part=1.0),
+                          "ViT-B/16 shape with the cross-correlation marginals of eval_attn_diml.py's calc_similarity call "
+                          "(use_inverse T=0.1, cls centres), 4096-image synthetic gallery")
 METRIC = "reranked query-candidate pairs/sec at K=100"
 FP32_LANES_PER_SM = 128
 
@@ -371,7 +374,7 @@ def main():
     scale = n / 100.0
     if (c, r) == (128, 49) and k <= 1024:
         kname = "pair_fused_kernel"
-    elif params.mode in ("rollout", "uniform") and params.ot_part > 0.999 and c % 16 == 0 and 20 <= r <= 224:
+    elif params.ot_part > 0.999 and c % 16 == 0 and 20 <= r <= 224:
         kname = "generic_fused_kernel"          # S3 + S4 in one kernel from the operand copy (generic_fused.cu)
     else:
         kname = "generic_sim_mma_kernel + generic_sk_chunk_kernel + generic_finish_kernel"

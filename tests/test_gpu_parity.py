@@ -445,7 +445,7 @@ def test_generic_fused_equals_separate_kernels(eng, c, r, k, nq, monkeypatch):
     kernels of generic_ot.cu (VR_GENERIC_FUSED=0): the same K, the same FMA chains and the same stop arithmetic, so the
     iteration counts must be IDENTICAL and the scores equal up to the order of the final sum -- for loops that stop in
     the first pass of 8 iterations, in a later one (the work list), or never (max_iter not a multiple of 8), padded
-    shortlist entries, more candidates per query than SMs, rollout and uniform marginals."""
+    shortlist entries, more candidates per query than SMs, every marginal mode."""
     from vitrerank.engine import OTParams
     n = max(60, k + 20)
     g = synth.make_gallery(n, c, r, classes=5, seed=c + r, sigma=0.6)
@@ -455,7 +455,10 @@ def test_generic_fused_equals_separate_kernels(eng, c, r, k, nq, monkeypatch):
     idx[1, k - 2:] = -1                                   # padded entries take no part in the stop test and score 0
     longest = 0
     for p in (OTParams(mode="rollout"), OTParams(mode="uniform"), OTParams(mode="rollout", thresh=1e-6),
-              OTParams(mode="rollout", thresh=1e-9, max_iter=19), OTParams(mode="uniform", ot_temp=0.1, thresh=1e-5, max_iter=40)):
+              OTParams(mode="rollout", thresh=1e-9, max_iter=19), OTParams(mode="uniform", ot_temp=0.1, thresh=1e-5, max_iter=40),
+              # cross-correlation marginals (generic_prepare_kernel writes them, marginals only, before the fused kernel)
+              OTParams(mode="inverse", temperature=0.1, use_cls_token=True), OTParams(mode="relu"), OTParams(mode="soft", thresh=1e-3),
+              OTParams(mode="minus", use_cls_token=True, thresh=1e-4)):
         monkeypatch.delenv("VR_GENERIC_FUSED", raising=False)
         s1, n1 = eng.rerank_scores(idx, k, p, q_start=2, q_stride=3)
         monkeypatch.setenv("VR_GENERIC_FUSED", "0")

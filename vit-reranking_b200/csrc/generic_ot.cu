@@ -84,8 +84,10 @@ __global__ void __launch_bounds__(GP_THREADS) generic_prepare_kernel(GenArgs a) 
             a.rv[pair * Re + i] = 0.f;
             a.cv[pair * Re + i] = 0.f;
         }
-        for (int i = tid; i < Re * Re; i += GP_THREADS) a.K[pair * Re * Re + i] = 0.f;
-        for (int i = tid; i < R * R; i += GP_THREADS) a.sim[pair * R * R + i] = 0.f;
+        if (a.K)   // (nullptr: marginals only, for generic_fused.cu)
+            for (int i = tid; i < Re * Re; i += GP_THREADS) a.K[pair * Re * Re + i] = 0.f;
+        if (a.sim)
+            for (int i = tid; i < R * R; i += GP_THREADS) a.sim[pair * R * R + i] = 0.f;
         if (tid == 0) a.e[pair] = -1.f;  // marks the pair as skipped for iterate / decide
         return;
     }
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(GP_THREADS) generic_prepare_kernel(GenArgs a) 
                 }
         }
     }
-    if (!full) {  // utilities/diml.py:62-73
+    if (!full && a.K) {  // utilities/diml.py:62-73
         for (int i = tid; i < R; i += GP_THREADS) {
             Ko[(int64_t)i * Re + R] = bins;
             Ko[(int64_t)R * Re + i] = bins;
@@ -442,8 +444,8 @@ struct GenWs {
     size_t bytes;
 };
 
-// mode 0: the direct Sinkhorn call (K, u, v are the caller's); 1: the rerank path; 2: generic_fused_rerank only (no sim, K or state history:
-// rhist holds the per-iteration scores)
+// mode 0: the direct Sinkhorn call (K, u, v are the caller's); 1: the rerank path; 2: generic_fused_rerank only (u and v for the
+// cross-correlation marginals, but no sim, K or state history: rhist holds the per-iteration scores)
 static GenWs carve(void* base, int64_t nq, int64_t np, int r, int rows, int cols, int mode) {
     const bool with_sim = mode == 1;
     GenWs w{};
@@ -455,8 +457,8 @@ static GenWs carve(void* base, int64_t nq, int64_t np, int r, int rows, int cols
     };
     w.sim = reinterpret_cast<float*>(take(with_sim ? (size_t)np * r * r * 4 : 0));
     w.K = reinterpret_cast<float*>(take(with_sim ? (size_t)np * rows * cols * 4 : 0));
-    w.u = reinterpret_cast<float*>(take(with_sim ? (size_t)np * rows * 4 : 0));
-    w.v = reinterpret_cast<float*>(take(with_sim ? (size_t)np * cols * 4 : 0));
+    w.u = reinterpret_cast<float*>(take(mode ? (size_t)np * rows * 4 : 0));
+    w.v = reinterpret_cast<float*>(take(mode ? (size_t)np * cols * 4 : 0));
     w.rv = reinterpret_cast<float*>(take((size_t)np * rows * 4));
     w.cv = reinterpret_cast<float*>(take((size_t)np * cols * 4));
     w.e = reinterpret_cast<float*>(take((size_t)np * 4));
@@ -476,7 +478,7 @@ size_t generic_rerank_workspace_bytes(int64_t nq, int k, int r, const vr_ot_para
 }
 
 // What generic_rerank needs when it takes generic_fused.cu (a.packed set, scores only, generic_fused_supported): 1.6 KB per pair
-// instead of 2 R^2 floats.
+// instead of 2 R^2 floats.  (3.2 KB with the marginal buffers.)
 size_t generic_fused_workspace_bytes(int64_t nq, int k, int r) { return carve(nullptr, nq, nq * k, r, r, r, 2).bytes; }
 
 size_t generic_sinkhorn_workspace_bytes(int64_t b, int m, int n) { return carve(nullptr, 1, b, 0, m, n, 0).bytes; }
@@ -968,6 +970,16 @@ int generic_rerank(GenArgs a, void* ws, size_t ws_bytes, cudaStream_t st) {
     a.sim_done = 0;
     if (fused) {
         // registered bank with its operand copy, scores only: S3 and S4 in one kernel, nothing but the scores leaves the SMs
+        if (a.p.mode >= VR_MODE_INVERSE) {   // cross-correlation marginals come from the fp32 rows: generic_prepare_kernel, marginals only
+            a.sim = nullptr;
+            a.K = nullptr;
+            a.sim_done = 1;
+            size_t smem_p = (size_t)(2 * GP_KC * GP_T + 32 + 2 * a.c + 2 * a.r) * 4;
+            if (smem_p > 48 * 1024)
+                VR_CHECK_CUDA(cudaFuncSetAttribute(generic_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+            generic_prepare_kernel<<<(unsigned)np, GP_THREADS, smem_p, st>>>(a);
+            VR_LAUNCH_CHECK();
+        }
         int rc = generic_fused_rerank(a, w.done, w.tstar, reinterpret_cast<int32_t*>(w.e), w.ehist, w.rhist, w.niter, st);
         if (rc) return rc;
         if (a.out_niter) {
