@@ -178,14 +178,67 @@ __global__ void __launch_bounds__(GP_THREADS) generic_prepare_kernel(GenArgs a) 
             gcs[c] = gcs[c] / dg;
         }
         __syncthreads();
-        for (int s = tid; s < R; s += GP_THREADS) {
-            float x = 0.f, y = 0.f;
-            for (int c = 0; c < C; c++) {
-                x = fmaf(qcs[c], Fg[(int64_t)c * R + s], x);
-                y = fmaf(Ag[(int64_t)c * R + s], gcs[c], y);
+        if (a.cc_stages > 0) {
+            // The two mat-vecs read both fp32 images once (1.2 MB at C = 768, R = 196): the 16 channel rows of a chunk are contiguous
+            // in both banks, so one thread streams them through a ring of bulk copies while every thread extends its two chains --
+            // the same FMA order as the loop below, at the speed the rows arrive instead of a dependent global load per FMA.
+            const int NS = a.cc_stages, NCH = C / GP_KC;
+            const uint32_t chunk_bytes = (uint32_t)(GP_KC * R * 4);
+            float* ring = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ccv + R) + 15) & ~(uintptr_t)15);   // [NS][2][16 * R]
+            uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)NS * 2 * GP_KC * R);   // [NS]
+            if (tid == 0) {
+                for (int i = 0; i < NS; i++) mbar_init(full + i, 1);
+                fence_mbar_init();
             }
-            ccu[s] = x;
-            ccv[s] = y;
+            __syncthreads();
+            if (tid == 0)
+                for (int i = 0; i < NS && i < NCH; i++) {
+                    mbar_expect_tx(full + i, 2 * chunk_bytes);
+                    bulk_g2s(ring + (size_t)(2 * i) * GP_KC * R, Fg + (int64_t)i * GP_KC * R, chunk_bytes, full + i);
+                    bulk_g2s(ring + (size_t)(2 * i + 1) * GP_KC * R, Ag + (int64_t)i * GP_KC * R, chunk_bytes, full + i);
+                }
+            float xs[4] = {0.f, 0.f, 0.f, 0.f}, ys[4] = {0.f, 0.f, 0.f, 0.f};   // R <= 1,024: up to 4 patches per thread
+            for (int ch = 0; ch < NCH; ch++) {
+                const int stg = ch % NS;
+                mbar_wait(full + stg, (uint32_t)(ch / NS) & 1u);
+                const float* Fr = ring + (size_t)(2 * stg) * GP_KC * R;
+                const float* Ar = Fr + (size_t)GP_KC * R;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int s = tid + j * GP_THREADS;
+                    if (s < R) {
+#pragma unroll
+                        for (int kk = 0; kk < GP_KC; kk++) {
+                            xs[j] = fmaf(qcs[ch * GP_KC + kk], Fr[kk * R + s], xs[j]);
+                            ys[j] = fmaf(Ar[kk * R + s], gcs[ch * GP_KC + kk], ys[j]);
+                        }
+                    }
+                }
+                __syncthreads();   // the stage is free
+                if (tid == 0 && ch + NS < NCH) {
+                    mbar_expect_tx(full + stg, 2 * chunk_bytes);
+                    bulk_g2s(ring + (size_t)(2 * stg) * GP_KC * R, Fg + (int64_t)(ch + NS) * GP_KC * R, chunk_bytes, full + stg);
+                    bulk_g2s(ring + (size_t)(2 * stg + 1) * GP_KC * R, Ag + (int64_t)(ch + NS) * GP_KC * R, chunk_bytes, full + stg);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int s = tid + j * GP_THREADS;
+                if (s < R) {
+                    ccu[s] = xs[j];
+                    ccv[s] = ys[j];
+                }
+            }
+        } else {
+            for (int s = tid; s < R; s += GP_THREADS) {
+                float x = 0.f, y = 0.f;
+                for (int c = 0; c < C; c++) {
+                    x = fmaf(qcs[c], Fg[(int64_t)c * R + s], x);
+                    y = fmaf(Ag[(int64_t)c * R + s], gcs[c], y);
+                }
+                ccu[s] = x;
+                ccv[s] = y;
+            }
         }
         __syncthreads();
     }
@@ -926,6 +979,22 @@ static int run_iterations(const IterArgs& it, const GenWs& w, int64_t nq, int64_
     return VR_OK;
 }
 
+// Shared memory of generic_prepare_kernel; decides whether the cross-correlation rows go through the bulk-copy ring (a.cc_stages).
+static size_t prepare_smem(GenArgs& a) {
+    const size_t base = (size_t)(2 * GP_KC * GP_T + 32 + 2 * a.c + 2 * a.r) * 4;
+    a.cc_stages = 0;
+    const char* e = getenv("VR_GENERIC_CC");
+    if (a.p.mode < VR_MODE_INVERSE || (e && e[0] == 'l') || a.c % GP_KC != 0 || a.r > 4 * GP_THREADS ||
+        ((reinterpret_cast<uintptr_t>(a.q_patches) | reinterpret_cast<uintptr_t>(a.c_patches)) & 15) != 0)
+        return base;
+    const size_t stage = (size_t)2 * GP_KC * a.r * 4;
+    int ns = 4;
+    while (ns > 1 && base + 16 + ns * stage + ns * 8 > 100 * 1024) ns--;   // two CTAs per SM
+    if (base + 16 + ns * stage + ns * 8 > 100 * 1024) return base;
+    a.cc_stages = ns;
+    return base + 16 + ns * stage + ns * 8;
+}
+
 int generic_rerank(GenArgs a, void* ws, size_t ws_bytes, cudaStream_t st) {
     VR_REQUIRE(a.nq > 0 && a.k > 0, "generic_rerank: empty problem");
     VR_REQUIRE(a.c >= 1 && a.r >= 1 && a.r <= 1024 && a.c <= 4096, "generic_rerank: unsupported shape C=%d R=%d", a.c,
@@ -974,7 +1043,7 @@ int generic_rerank(GenArgs a, void* ws, size_t ws_bytes, cudaStream_t st) {
             a.sim = nullptr;
             a.K = nullptr;
             a.sim_done = 1;
-            size_t smem_p = (size_t)(2 * GP_KC * GP_T + 32 + 2 * a.c + 2 * a.r) * 4;
+            const size_t smem_p = prepare_smem(a);
             if (smem_p > 48 * 1024)
                 VR_CHECK_CUDA(cudaFuncSetAttribute(generic_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
             generic_prepare_kernel<<<(unsigned)np, GP_THREADS, smem_p, st>>>(a);
@@ -993,7 +1062,7 @@ int generic_rerank(GenArgs a, void* ws, size_t ws_bytes, cudaStream_t st) {
         if (rc) return rc;
         a.sim_done = 1;
     }
-    size_t smem = (size_t)(2 * GP_KC * GP_T + 32 + 2 * a.c + 2 * a.r) * 4;
+    const size_t smem = prepare_smem(a);
     if (smem > 48 * 1024)
         VR_CHECK_CUDA(cudaFuncSetAttribute(generic_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     generic_prepare_kernel<<<(unsigned)np, GP_THREADS, smem, st>>>(a);

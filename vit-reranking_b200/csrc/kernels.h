@@ -43,6 +43,8 @@ struct GenArgs {
     vr_ot_params p;
     float part_bin;   // 1 - ot_part as the reference rounds it (set by generic_rerank)
     const void* packed; // re-packed registered bank for generic_sim_mma (generic_repack), both roles; nullptr: convert per pair
+    int cc_stages;    // > 0: generic_prepare_kernel streams the fp32 rows for the cross-correlation marginals through a ring of this many
+                      // bulk-copy stages (set by generic_rerank)
     int sim_done;     // sim and K were written by generic_sim_mma (tensor cores): generic_prepare_kernel skips its fp32 loop
     // workspace
     float* sim;    // [np, r, r]
