@@ -456,18 +456,26 @@ def test_generic_fused_equals_separate_kernels(eng, c, r, k, nq, monkeypatch):
     longest = 0
     for p in (OTParams(mode="rollout"), OTParams(mode="uniform"), OTParams(mode="rollout", thresh=1e-6),
               OTParams(mode="rollout", thresh=1e-9, max_iter=19), OTParams(mode="uniform", ot_temp=0.1, thresh=1e-5, max_iter=40),
-              # cross-correlation marginals (generic_prepare_kernel writes them, marginals only, before the fused kernel)
-              OTParams(mode="inverse", temperature=0.1, use_cls_token=True), OTParams(mode="relu"), OTParams(mode="soft", thresh=1e-3),
-              OTParams(mode="minus", use_cls_token=True, thresh=1e-4)):
+              # cross-correlation marginals, centres = patch means: generic_prepare_kernel writes them (marginals only) first
+              OTParams(mode="relu"), OTParams(mode="soft", thresh=1e-3), OTParams(mode="inverse", temperature=0.1),
+              # ... with cls centres: they come out of the MMA itself (the operand copy carries the centre as patch R), so the
+              # marginals carry the split's 3e-7 instead of the fp32 chain's 1e-7: a stop test may flip in a borderline query
+              OTParams(mode="inverse", temperature=0.1, use_cls_token=True), OTParams(mode="relu", use_cls_token=True),
+              OTParams(mode="soft", use_cls_token=True, thresh=1e-3), OTParams(mode="minus", use_cls_token=True, thresh=1e-4)):
         monkeypatch.delenv("VR_GENERIC_FUSED", raising=False)
         s1, n1 = eng.rerank_scores(idx, k, p, q_start=2, q_stride=3)
         monkeypatch.setenv("VR_GENERIC_FUSED", "0")
         s0, n0 = eng.rerank_scores(idx, k, p, q_start=2, q_stride=3)
         monkeypatch.delenv("VR_GENERIC_FUSED", raising=False)
-        assert torch.equal(n1, n0), (p, n1, n0)
+        in_mma = p.use_cls_token and p.mode in ("inverse", "relu", "soft", "minus")
+        same = (n1 == n0)
+        if in_mma:
+            assert int((n1 - n0).abs().max()) <= 1 and same.float().mean() >= 0.75, (p, n1, n0)
+        else:
+            assert bool(same.all()), (p, n1, n0)
         assert (s1[1, k - 2:] == 0).all() and (s0[1, k - 2:] == 0).all()
-        err = ((s1 - s0).abs() / s0.abs().clamp_min(1e-6)).max().item()
-        assert err < 2e-6, (p, err)
+        err = ((s1 - s0).abs() / s0.abs().clamp_min(1e-6))[same].max().item()
+        assert err < (2e-5 if in_mma else 2e-6), (p, err)
         longest = max(longest, int(n1.max()))
     assert longest > 16                                   # (some case ran into the third pass)
 

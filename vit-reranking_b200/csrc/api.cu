@@ -428,10 +428,11 @@ static int rerank_scores_impl(vr_ctx* ctx, const float* q_patches, const float* 
         void* gp = generic_operand_copy(ctx);
         if (gp) {
             if (!ctx->gpacked_valid) {
-                if ((rc = generic_repack(ctx->patches, ctx->n, ctx->c, ctx->r, gp, st))) return rc;
+                if ((rc = generic_repack(ctx->patches, ctx->centers, ctx->n, ctx->c, ctx->r, gp, st))) return rc;
                 ctx->gpacked_valid = true;
             }
             g.packed = gp;
+            g.packed_centers = ctx->centers && (ctx->r % 16) != 0;
         }
     }
     return generic_rerank(g, workspace, workspace_bytes, st);

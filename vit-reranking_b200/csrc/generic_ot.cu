@@ -1039,7 +1039,8 @@ int generic_rerank(GenArgs a, void* ws, size_t ws_bytes, cudaStream_t st) {
     a.sim_done = 0;
     if (fused) {
         // registered bank with its operand copy, scores only: S3 and S4 in one kernel, nothing but the scores leaves the SMs
-        if (a.p.mode >= VR_MODE_INVERSE) {   // cross-correlation marginals come from the fp32 rows: generic_prepare_kernel, marginals only
+        if (a.p.mode >= VR_MODE_INVERSE && !(a.packed_centers && a.p.use_cls_token)) {
+            // cross-correlation marginals from the fp32 rows (centres = patch means): generic_prepare_kernel, marginals only
             a.sim = nullptr;
             a.K = nullptr;
             a.sim_done = 1;

@@ -256,8 +256,9 @@ struct G3PArgs {
     float* K;
 };
 
-__global__ void __launch_bounds__(256) generic_repack_kernel(const float* __restrict__ patches, int64_t first, int c, int r, int rp16,
-                                                             unsigned char* __restrict__ packed) {
+__global__ void __launch_bounds__(256) generic_repack_kernel(const float* __restrict__ patches, const float* __restrict__ centers,
+                                                             int64_t first, int c, int r, int rp16, unsigned char* __restrict__ packed) {
+    extern __shared__ float rp_cn[];   // [c]: the image's centre, L2-normalised (+ 32 floats for the reduction)
     const int64_t im = first + blockIdx.x;
     const float* F = patches + im * (int64_t)c * r;
     const uint32_t run = (uint32_t)rp16 * 16u;   // one (plane, k-core) run
@@ -275,6 +276,41 @@ __global__ void __launch_bounds__(256) generic_repack_kernel(const float* __rest
         unsigned char* blk = out + (size_t)ch * (4u * run) + (uint32_t)g * run + (uint32_t)(s >> 3) * 128u + (uint32_t)(s & 7) * 16u;
         *reinterpret_cast<uint4*>(blk) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<uint4*>(blk + 2u * run) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+    // Patch R (a spare padding row when R % 16 != 0): the image's normalised centre.  In the MMA it turns row R of sim into
+    // <candidate centre, query patches> and column R into <query centre, candidate patches> -- the cross-correlations of
+    // utilities/diml.py:104-133 with use_cls_token -- at no cost (generic_fused.cu).
+    if (centers && r < rp16) {
+        float* red = rp_cn + c;
+        const float* g = centers + im * (int64_t)c;
+        float ng = 0.f;
+        for (int cc = threadIdx.x; cc < c; cc += 256) {
+            const float x = g[cc];
+            rp_cn[cc] = x;
+            ng += x * x;
+        }
+        {   // generic_prepare_kernel's block sum
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            ng = warp_sum(ng);
+            __syncthreads();
+            if (lane == 0) red[warp] = ng;
+            __syncthreads();
+            ng = 0.f;
+            for (int i = 0; i < 8; i++) ng += red[i];
+        }
+        const float dg = fmaxf(sqrtf(ng), 1e-12f);
+        for (int item = threadIdx.x; item < nch * 2; item += 256) {
+            const int ch = item >> 1, g2 = item & 1;
+            float x[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) x[e] = rp_cn[ch * 16 + 8 * g2 + e] / dg;
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int w = 0; w < 4; w++) g3_split(x[2 * w], x[2 * w + 1], hi[w], lo[w]);
+            unsigned char* blk = out + (size_t)ch * (4u * run) + (uint32_t)g2 * run + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
+            *reinterpret_cast<uint4*>(blk) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(blk + 2u * run) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
     }
 }
 
@@ -415,10 +451,10 @@ size_t generic_packed_image_bytes(int c, int r) {
     return (size_t)(c / 16) * (rp16 * 64);
 }
 
-int generic_repack(const float* patches, int64_t n, int c, int r, void* packed, cudaStream_t st) {
+int generic_repack(const float* patches, const float* centers, int64_t n, int c, int r, void* packed, cudaStream_t st) {
     const int rp16 = (r + 15) / 16 * 16;
     VR_CHECK_CUDA(cudaMemsetAsync(packed, 0, (size_t)n * generic_packed_image_bytes(c, r), st));
-    generic_repack_kernel<<<(unsigned)n, 256, 0, st>>>(patches, 0, c, r, rp16, reinterpret_cast<unsigned char*>(packed));
+    generic_repack_kernel<<<(unsigned)n, 256, (size_t)(c + 32) * 4, st>>>(patches, centers, 0, c, r, rp16, reinterpret_cast<unsigned char*>(packed));
     VR_LAUNCH_CHECK();
     return VR_OK;
 }

@@ -43,6 +43,7 @@ struct GenArgs {
     vr_ot_params p;
     float part_bin;   // 1 - ot_part as the reference rounds it (set by generic_rerank)
     const void* packed; // re-packed registered bank for generic_sim_mma (generic_repack), both roles; nullptr: convert per pair
+    int packed_centers; // the operand copy carries every image's normalised centre as patch R (R % 16 != 0)
     int cc_stages;    // > 0: generic_prepare_kernel streams the fp32 rows for the cross-correlation marginals through a ring of this many
                       // bulk-copy stages (set by generic_rerank)
     int sim_done;     // sim and K were written by generic_sim_mma (tensor cores): generic_prepare_kernel skips its fp32 loop
@@ -106,7 +107,7 @@ int generic_sinkhorn(const float* K, const float* u, const float* v, int64_t b, 
 bool generic_sim_mma_supported(int c, int r);
 int generic_sim_mma(const GenArgs& g, int re, cudaStream_t st);
 size_t generic_packed_image_bytes(int c, int r);
-int generic_repack(const float* patches, int64_t n, int c, int r, void* packed, cudaStream_t st);
+int generic_repack(const float* patches, const float* centers, int64_t n, int c, int r, void* packed, cudaStream_t st);
 
 // generic_fused.cu: S3 + S4 in one kernel from the re-packed bank (full OT, rollout / uniform marginals, scores only)
 bool generic_fused_supported(int c, int r, const vr_ot_params* p);
