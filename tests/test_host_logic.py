@@ -333,3 +333,15 @@ def test_partial_ot_pad_is_the_reference_rounding():
     for part in (0.123456, 0.3333333, 1 / 3, 0.7071067811865476):
         got = np.float32(_lib.lib.vr_partial_ot_pad(C.c_float(part)))
         assert abs(float(got) - (1 - part)) < 1e-7
+
+
+def test_rollout_workspace_is_the_fused_map():
+    """vr_rollout_block_workspace_bytes (host arithmetic, no GPU): the fused [b, ht * wt] map, the per-image histograms and the
+    union mask -- the select runs over the WHOLE map, cls row and column included (eval_cvt_diml.py:74-108 filters before :57-58 drops)."""
+    from vitrerank import _lib
+    f = _lib.lib.vr_rollout_block_workspace_bytes
+    for b, ht, wt in ((1, 50, 50), (64, 197, 197), (8, 3136, 784)):
+        n = f(b, ht, wt, 0)
+        assert n == f(b, ht, wt, 1)
+        assert b * ht * wt * 4 + ht * wt <= n <= b * ht * wt * 4 + ht * wt + b * 2048 * 4 + b * 16 + 2048
+    assert f(0, 50, 50, 0) == 0
