@@ -93,8 +93,8 @@ __global__ void __launch_bounds__(GP_THREADS) generic_prepare_kernel(GenArgs a) 
     }
     const float* Ag = a.q_patches + qid * (int64_t)C * R;
     const float* Fg = a.c_patches + (int64_t)cand * C * R;
-    float* simo = a.sim + pair * (int64_t)R * R;
-    float* Ko = a.K + pair * (int64_t)Re * Re;
+    float* simo = a.sim ? a.sim + pair * (int64_t)R * R : nullptr;   // (nullptr: marginals only, for generic_fused.cu)
+    float* Ko = a.K ? a.K + pair * (int64_t)Re * Re : nullptr;
 
     // ---- sim[s][m] = sum_c F[c][s] * A[c][m], K = exp(-(1 - sim) / ot_temp) ----
     const int tx = tid & 15, ty = tid >> 4;
