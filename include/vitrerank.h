@@ -97,7 +97,9 @@ VR_API int vr_bank_register(vr_ctx* ctx, const float* patches, const float* cent
 /* Derives the library-owned operand copy of images [first, first + count) of the registered bank now, on `stream`
  * (ranges in ascending order without gaps; once [0, n) is covered the fused rerank uses the copy as it is).  Lets a caller
  * that fills the bank piecewise (uploads, all-gathers) overlap the re-pack with the transfers and with stage 0; later
- * rerank calls must be ordered after it by the caller (same stream or an event).  No-op for shapes without a fused kernel. */
+ * rerank calls must be ordered after it by the caller (same stream or an event).  The copy also carries every image's normalised
+ * centre (the cross-correlation marginals then come out of the patch-similarity MMA): patches AND centres of the range must be
+ * valid on `stream`.  No-op for shapes without a fused kernel. */
 VR_API int vr_bank_prepare(vr_ctx* ctx, int64_t first, int64_t count, void* stream);
 
 /* Bank ingest: the step between the backbone and the path (evaluation/eval_cvt_diml.py:269-278 head output -> permute ->

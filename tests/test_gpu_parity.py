@@ -580,10 +580,12 @@ def test_sinkhorn_bit_exact_given_inputs(eng, b, r, sigma):
 
 @pytest.mark.parametrize("mode,kw", [("rollout", {}), ("inverse", dict(temperature=0.1, use_cls_token=True)),
                                      ("minus", dict(use_cls_token=False))])
-def test_packed_bank_path_equals_direct_path(eng, mode, kw):
+def test_packed_bank_path_equals_direct_path(eng, mode, kw, monkeypatch):
     """A registered bank is re-packed once into fp16 hi / lo operand planes and S3 is fed by TMA; direct calls with
     unregistered tensors split the fp32 rows on the fly.  Both feed the tensor cores the same bits, so scores and
-    iteration counts must be identical, not just close."""
+    iteration counts must be identical, not just close.  (VR_PAIR_CC=fp32: with cls centres the registered path would
+    otherwise take its cross-correlations out of the MMA, test_cross_correlations_out_of_the_mma.)"""
+    monkeypatch.setenv("VR_PAIR_CC", "fp32")
     n, k = 150, 100
     g = synth.make_gallery(n, 128, 49, classes=5, seed=31, sigma=0.6)
     eng.register(g.patches, g.centers, g.rollout, g.labels)
@@ -596,6 +598,41 @@ def test_packed_bank_path_equals_direct_path(eng, mode, kw):
                                         q_rollout=g.rollout[q], c_rollout=g.rollout[idx_c[q]], want_uv=False)
         assert int(n2) == int(niter[q])
         assert torch.equal(s2.cpu(), score[q].cpu())
+
+
+@pytest.mark.parametrize("mode,kw", [("inverse", dict(temperature=0.1)), ("minus", {}), ("relu", {}), ("soft", {})])
+def test_cross_correlations_out_of_the_mma(eng, mode, kw, monkeypatch):
+    """With cls centres the operand copy of a registered bank carries every image's normalised centre as patch 50, so
+    accumulator row / column 50 of the patch-similarity MMA ARE the cross-correlations <candidate centre, query patches>
+    and <query centre, candidate patches> (utilities/diml.py:104-133): no second pass over the fp32 bank (VR_PAIR_CC=fp32).
+    They carry the split's 3e-7 instead of the fp32 chain's 1e-7 -- the noise the Gibbs kernel already has -- so on a
+    well-conditioned gallery (the Cars196-shaped one) most queries keep their iteration count, the others move by one, and
+    where the count is kept every score agrees to 2e-5; K = 100 and the wide K = 300 groups, gallery queries and outside queries."""
+    g = synth.make_named("cars196", seed=0, n=1560)
+    sub = slice(0, 1500)
+    eng.register(g.patches[sub], g.centers[sub], g.rollout[sub], g.labels[sub])
+    p = params(mode=mode, use_cls_token=True, **kw)
+    for k, nq in ((100, 300), (300, 40)):
+        idx, _ = eng.stage0_topk(k, q_start=0, q_stride=5, nq=nq)
+        monkeypatch.delenv("VR_PAIR_CC", raising=False)
+        s1, n1 = eng.rerank_scores(idx, k, p, q_start=0, q_stride=5)
+        monkeypatch.setenv("VR_PAIR_CC", "fp32")
+        s0, n0 = eng.rerank_scores(idx, k, p, q_start=0, q_stride=5)
+        same = n1 == n0
+        assert same.float().mean() >= 0.75, (mode, k, same.float().mean().item())   # (relu: many marginal entries at 0, the touchiest)
+        assert int((n1 - n0).abs().max()) <= 1, (mode, k, (n1 - n0).abs().max().item())
+        rel = ((s1 - s0).abs() / s0.abs().clamp_min(1e-9))[same]
+        assert rel.max().item() < 2e-5, (mode, k, rel.max().item())
+    # queries that are not gallery items (training_tools/val.py:159-190): their operand copy is packed per call, centres included
+    qs = slice(1500, 1560)
+    idx, _ = eng.stage0_topk(100, q_centers=g.centers[qs])
+    monkeypatch.delenv("VR_PAIR_CC", raising=False)
+    s1, n1 = eng.rerank_scores_queries(g.patches[qs], g.centers[qs], idx, 100, p)
+    monkeypatch.setenv("VR_PAIR_CC", "fp32")
+    s0, n0 = eng.rerank_scores_queries(g.patches[qs], g.centers[qs], idx, 100, p)
+    same = n1 == n0
+    assert same.float().mean() >= 0.75 and int((n1 - n0).abs().max()) <= 1
+    assert ((s1 - s0).abs() / s0.abs().clamp_min(1e-9))[same].max().item() < 2e-5
 
 
 def test_exchange_transports_agree(eng, monkeypatch):

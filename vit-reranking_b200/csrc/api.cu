@@ -43,6 +43,7 @@ struct vr_ctx {
     cudaStream_t copy_stream = nullptr;   // uploads the patch bank piece by piece while stage 0 runs (vr_evaluate_host)
     cudaStream_t prep_stream = nullptr;   // re-packs every piece as it lands, under the upload of the next one
     cudaEvent_t piece_ready[8] = {};      // recorded on copy_stream after each piece
+    cudaEvent_t small_ready = nullptr;    // recorded on own_stream after the centres / rollout / labels of vr_evaluate_host went up
     cudaEvent_t patches_ready = nullptr;  // recorded on prep_stream; non-null pending_wait makes the next rerank wait for it
     bool pending_wait = false;
     float* dbg_err = nullptr;  // see vr_debug_err_trace
@@ -119,7 +120,8 @@ int vr_create(int device, vr_ctx** out) {
     rc = (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
           cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
           cudaStreamCreateWithFlags(&ctx->prep_stream, cudaStreamNonBlocking) == cudaSuccess &&
-          cudaEventCreateWithFlags(&ctx->patches_ready, cudaEventDisableTiming) == cudaSuccess)
+          cudaEventCreateWithFlags(&ctx->patches_ready, cudaEventDisableTiming) == cudaSuccess &&
+          cudaEventCreateWithFlags(&ctx->small_ready, cudaEventDisableTiming) == cudaSuccess)
              ? VR_OK
              : VR_E_CUDA;
     for (int i = 0; i < 8 && rc == VR_OK; i++)
@@ -146,6 +148,7 @@ int vr_destroy(vr_ctx* ctx) {
     for (int i = 0; i < 8; i++)
         if (ctx->piece_ready[i]) cudaEventDestroy(ctx->piece_ready[i]);
     if (ctx->patches_ready) cudaEventDestroy(ctx->patches_ready);
+    if (ctx->small_ready) cudaEventDestroy(ctx->small_ready);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     pair_fused_ctx_close(ctx->device);
     delete ctx;
@@ -216,7 +219,7 @@ int vr_bank_prepare(vr_ctx* ctx, int64_t first, int64_t count, void* stream) {
     void* packed = nullptr;
     int rc = arena_get(ctx, "packed", pair_fused_packed_bytes(ctx->n), &packed);
     if (rc) return rc;
-    if ((rc = pair_fused_repack(ctx->patches, ctx->n, first, count, packed, (cudaStream_t)stream))) return rc;
+    if ((rc = pair_fused_repack(ctx->patches, ctx->centers, ctx->n, first, count, packed, (cudaStream_t)stream))) return rc;
     ctx->packed_hi = std::max(ctx->packed_hi, first + count);
     if (ctx->packed_hi >= ctx->n) ctx->packed_valid = true;
     return VR_OK;
@@ -390,7 +393,7 @@ static int rerank_scores_impl(vr_ctx* ctx, const float* q_patches, const float* 
         void* packed = nullptr;
         if ((rc = arena_get(ctx, "packed", pair_fused_packed_bytes(ctx->n), &packed))) return rc;
         if (!ctx->packed_valid) {
-            if ((rc = pair_fused_repack(ctx->patches, ctx->n, 0, ctx->n, packed, st))) return rc;
+            if ((rc = pair_fused_repack(ctx->patches, ctx->centers, ctx->n, 0, ctx->n, packed, st))) return rc;
             ctx->packed_valid = true;
         }
         a.c_packed_a = packed;
@@ -398,9 +401,11 @@ static int rerank_scores_impl(vr_ctx* ctx, const float* q_patches, const float* 
         if (ext) {   // explicit query bank: its operand planes are derived per call
             void* packed_q = nullptr;
             if ((rc = arena_get(ctx, "packed_q", pair_fused_packed_bytes(nq), &packed_q))) return rc;
-            if ((rc = pair_fused_repack(q_patches, nq, 0, nq, packed_q, st))) return rc;
+            if ((rc = pair_fused_repack(q_patches, q_centers, nq, 0, nq, packed_q, st))) return rc;
             a.q_packed_b = (const char*)packed_q + pair_fused_packed_bytes(nq) / 2;
         }
+        // the operand copies carry the images' normalised centres (pack_image): cross-correlations with cls centres come out of the MMA
+        a.packed_centers = (ctx->centers && (!ext || q_centers) && !(getenv("VR_PAIR_CC") && getenv("VR_PAIR_CC")[0] == 'f')) ? 1 : 0;
         return pair_fused_launch(a, nq, st);
     }
     GenArgs g{};
@@ -683,6 +688,9 @@ int vr_evaluate_host(vr_ctx* ctx, const float* patches_host, const float* center
     VR_CHECK_CUDA(cudaMemcpyAsync(d_l, labels_host, (size_t)n * 8, cudaMemcpyHostToDevice, st));
     VR_CHECK_CUDA(cudaMemcpyAsync(d_c, centers_host, bc, cudaMemcpyHostToDevice, st));
     if (rollout_host) VR_CHECK_CUDA(cudaMemcpyAsync(d_r, rollout_host, br, cudaMemcpyHostToDevice, st));
+    // (the re-pack of a piece stores every image's centre in its operand copy: prep_stream needs the centres)
+    VR_CHECK_CUDA(cudaEventRecord(ctx->small_ready, st));
+    VR_CHECK_CUDA(cudaStreamWaitEvent(ctx->prep_stream, ctx->small_ready, 0));
     rc = vr_bank_register(ctx, (const float*)d_p, (const float*)d_c, (const float*)d_r, (const int64_t*)d_l,
                           (const int32_t*)d_np, n, c, r);
     if (rc) return rc;

@@ -27,6 +27,7 @@ struct PairArgs {
     float part_bin;           // partial OT: 1 - ot_part as the reference rounds it (set by pair_fused_launch)
     const void* c_packed_a;   // re-packed candidate bank (pair_fused_repack) or nullptr: convert on the fly
     const void* q_packed_b;   // re-packed query bank, indexed by the query id
+    int packed_centers;       // both operand copies carry the images' normalised centres as patch 50 (pack_image)
 };
 
 struct GenArgs {
@@ -91,7 +92,7 @@ int pair_exchange_end(cudaStream_t st);
 int pair_fused_ctx_open(int device);    // vr_create / vr_destroy: the last context on a device frees the exchange buffer
 void pair_fused_ctx_close(int device);
 size_t pair_fused_packed_bytes(int64_t n);   // both roles
-int pair_fused_repack(const float* patches, int64_t n, int64_t first, int64_t count, void* packed, cudaStream_t st);
+int pair_fused_repack(const float* patches, const float* centers, int64_t n, int64_t first, int64_t count, void* packed, cudaStream_t st);
 int bank_ingest(const float* tokens, const float* centers_raw, int channel_major, int64_t n, int64_t first, int64_t count, int h,
                 int w, int grid, int c, float* patches, float* centers, void* packed, cudaStream_t st);
 

@@ -149,6 +149,7 @@ def evaluate_host_sharded(engine, patches, centers, rollout, labels, trunc_nums,
             piece = buf[p * w * mp:(p + 1) * w * mp]
             dist.all_gather_into_tensor(piece.view(-1), piece[rank * mp:(rank + 1) * mp].view(-1))   # in place, NVLink
             st["gathered"][p].record(side)
+    prep.wait_stream(cur)                      # the re-pack stores every image's centre in its operand copy: centres first
     with torch.cuda.stream(prep):
         for p in range(pieces):
             prep.wait_event(st["gathered"][p])
